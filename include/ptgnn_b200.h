@@ -1,0 +1,144 @@
+/*
+ * ptgnn_b200 -- C ABI of the B200-native message-passing hot path of microsoft/ptgnn.
+ *
+ * The reference is pure Python; the native boundary its hot path crosses is the third-party
+ * torch_scatter operator (`torch_scatter.scatter`, called at
+ * ptgnn/neuralmodels/gnn/messagepassing/abstractmessagepassing.py:44-50) plus ATen ops.  This library
+ * replaces that boundary and the layer bodies above it.  Every entry point:
+ *   - is extern "C", takes plain pointers/sizes (no torch types),
+ *   - takes DEVICE pointers unless the parameter is marked [host],
+ *   - enqueues its work on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     and returns without synchronising (except the *_host entry points, which copy from/to host
+ *     buffers and synchronise before returning),
+ *   - returns PTGNN_OK (0) or a negative PTGNN_E_* code; ptgnn_b200_last_error() gives the message.
+ *
+ * Index dtype: the reference delivers int64 index tensors (graphneuralnetwork.py:461-467); the edge
+ * plan down-converts them once per minibatch to int32 (E, N < 2^31 is checked).
+ * Floating-point dtype: fp32 state/weights (entry points suffixed _f32); bf16 state variants are
+ * suffixed _bf16 (fp32 accumulation, like the reference's AMP path abstractmessagepassing.py:43-50).
+ */
+#ifndef PTGNN_B200_H_
+#define PTGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTGNN_B200_ABI_VERSION 1
+#define PTGNN_MAX_EDGE_TYPES 128 /* etype is stored as uint8 in the plan; 128 keeps launch params < 4 KB */
+
+enum {
+    PTGNN_OK = 0,
+    PTGNN_E_INVALID = -1,     /* bad argument (null pointer, unsupported dimension, ...) */
+    PTGNN_E_UNSUPPORTED = -2, /* valid reference configuration without a native kernel yet */
+    PTGNN_E_CUDA = -3,        /* CUDA runtime error (message in ptgnn_b200_last_error) */
+    PTGNN_E_WORKSPACE = -4,   /* workspace too small */
+    PTGNN_E_INDEX = -5        /* edge index out of [0, num_nodes) (only reported by *_host / validate calls) */
+};
+
+/* torch_scatter `reduce=` strings (torch_scatter.scatter). */
+enum { PTGNN_REDUCE_SUM = 0, PTGNN_REDUCE_MEAN = 1, PTGNN_REDUCE_MAX = 2, PTGNN_REDUCE_MIN = 3 };
+/* activations used by MlpMessagePassingLayer (mlpmessagepassing.py:20,26). */
+enum { PTGNN_ACT_NONE = 0, PTGNN_ACT_GELU = 1, PTGNN_ACT_TANH = 2, PTGNN_ACT_RELU = 3 };
+
+int ptgnn_b200_abi_version(void);
+const char *ptgnn_b200_last_error(void);
+/* Number of kernel launches issued by this library in this process (bench.py's "gpu_launches"). */
+int64_t ptgnn_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Edge plan -- replaces `torch.cat([adj[1] for adj in adjacency_lists])` (gatedmessagepassing.py:46,
+ * mlpmessagepassing.py:102-109) and the index->row grouping inside torch_scatter.scatter: a canonical,
+ * STABLE target-sorted CSR over the concatenated per-type edge lists, built once per minibatch and
+ * reused by every layer.  Edge id e = position in cat(types) order.
+ *   row_ptr[N+1]     CSR offsets over targets
+ *   perm[E]          sorted position j -> edge id (stable: per target, edge-id ascending)
+ *   pos[E]           edge id -> sorted position
+ *   src_sorted[E]    source node of the edge at sorted position j
+ *   etype_sorted[E]  edge type of the edge at sorted position j
+ *   src32/tgt32[E]   the int64 inputs down-converted, edge-id order
+ *   status[1]        number of out-of-range indices seen (they are clamped to 0); 0 = valid
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptgnn_b200_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int ptgnn_b200_plan_build(int64_t num_nodes, int32_t num_types,
+                          const int64_t *const *src_ptrs /*[host] T device pointers*/,
+                          const int64_t *const *tgt_ptrs /*[host] T device pointers*/,
+                          const int64_t *counts /*[host] T edge counts*/, int32_t *row_ptr, int32_t *perm,
+                          int32_t *pos, int32_t *src_sorted, uint8_t *etype_sorted, int32_t *src32, int32_t *tgt32,
+                          int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Segmented reduce -- replaces torch_scatter.scatter(src, index, dim=0, dim_size=N, reduce) as called
+ * at abstractmessagepassing.py:44-50.  `messages` is [E, D] fp32.  If `perm` is NULL the rows are
+ * already in plan order (row j belongs to the target whose CSR range contains j); otherwise row
+ * perm[j] is read for sorted position j (rows in edge-id order, as torch_scatter receives them).
+ * out [N, D] fp32: empty targets -> 0.  arg_out (optional, max/min only) [N, D] int64 = edge id of the
+ * winning message (first occurrence wins ties), E for empty targets (torch_scatter's sentinel).
+ * ---------------------------------------------------------------------------------------------- */
+int ptgnn_b200_segment_reduce_f32(const float *messages, const int32_t *row_ptr, const int32_t *perm,
+                                  int64_t num_nodes, int64_t num_edges, int32_t dim, int32_t reduce, float *out,
+                                  int64_t *arg_out, void *stream);
+
+/* One-shot torch_scatter.scatter drop-in: builds a single-type plan from the int64 `index` and reduces.
+ * workspace >= ptgnn_b200_scatter_workspace_bytes(N, E). */
+size_t ptgnn_b200_scatter_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, int64_t num_edges, int32_t dim, int64_t num_nodes,
+                           int32_t reduce, float *out, int64_t *arg_out, void *workspace, size_t workspace_bytes,
+                           void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GatedMessagePassingLayer.forward (gatedmessagepassing.py:37-69), eval mode, no edge features:
+ *   m_e = W_{t(e)} h_{src(e)} ; a_v = reduce_{e: tgt(e)=v} m_e ; h'_v = GRUCell(a_v, h_v)
+ * edge_weights: [host] array of T device pointers, each nn.Linear.weight [D, H] row-major.
+ * gru_*: nn.GRUCell parameters weight_ih [3H, D], weight_hh [3H, H], bias_ih/bias_hh [3H] (gate order r,z,n).
+ * type_off: [host] T+1 prefix offsets of the per-type edge counts (edge-id space).
+ * workspace >= ptgnn_b200_gated_workspace_bytes(...): message buffer [E, D] + aggregate [N, D] + packed GRU weights.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t state_dim, int32_t message_dim);
+int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, int32_t state_dim, int32_t message_dim,
+                                 int32_t num_types, const int64_t *type_off /*[host]*/, const int32_t *row_ptr,
+                                 const int32_t *pos, const int32_t *src32,
+                                 const float *const *edge_weights /*[host] T device pointers*/, const float *gru_w_ih,
+                                 const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh, int32_t reduce,
+                                 float *out_states, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MlpMessagePassingLayer.forward (mlpmessagepassing.py:68-117), eval mode, default message MLP
+ * (mlp_hidden_layers = 0: one bias-free Linear, mlp.py:65-74), string aggregator, no edge features:
+ *   m_e = W_{t(e)} [h_src ; h_tgt] ; a_v = reduce m_e ; h'_v = act2(W_d LN(act1(a_v)) + b_d)
+ * edge_weights[t]: [D, 2H] (or [D, H] when use_target_state == 0).  ln_weight/ln_bias NULL => no LayerNorm;
+ * dense_weight NULL => no dense layer (output dim = D).  dense_weight [Hout, D], dense_bias [Hout].
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t in_dim, int32_t message_dim,
+                                      int32_t out_dim);
+int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_nodes, int32_t in_dim, int32_t message_dim,
+                               int32_t out_dim, int32_t num_types, const int64_t *type_off /*[host]*/,
+                               const int32_t *row_ptr, const int32_t *pos, const int32_t *src32, const int32_t *tgt32,
+                               const float *const *edge_weights /*[host] T device pointers*/,
+                               int32_t use_target_state, int32_t reduce, int32_t message_activation,
+                               const float *ln_weight, const float *ln_bias, float ln_eps, const float *dense_weight,
+                               const float *dense_bias, int32_t dense_activation, float *out_states, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry point (used for the end-to-end measurement): all pointers are HOST
+ * memory; copies inputs to the device, builds the plan, runs `num_layers` GatedMessagePassingLayers
+ * (layer l uses weight set l; pass the same pointers to share weights), copies the final states back
+ * and synchronises.  Mirrors GraphNeuralNetwork.gnn's loop (graphneuralnetwork.py:121-131) for a
+ * homogeneous stack of gated layers.  Returns PTGNN_E_INDEX if an edge index is out of range.
+ * ---------------------------------------------------------------------------------------------- */
+int ptgnn_b200_gated_gnn_forward_host_f32(const float *node_states, int64_t num_nodes, int32_t state_dim,
+                                          int32_t num_types, const int64_t *const *src_ptrs,
+                                          const int64_t *const *tgt_ptrs, const int64_t *counts, int32_t num_layers,
+                                          const float *const *edge_weights /* num_layers*T host pointers [D,H] */,
+                                          const float *const *gru_w_ih, const float *const *gru_w_hh,
+                                          const float *const *gru_b_ih, const float *const *gru_b_hh,
+                                          int32_t reduce, float *out_states);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTGNN_B200_H_ */

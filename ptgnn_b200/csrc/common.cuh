@@ -1,0 +1,114 @@
+// Shared helpers for the ptgnn_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/ptgnn_b200.h"
+
+namespace ptgnn {
+
+// ---- error reporting ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+
+#define PTGNN_CHECK_ARG(cond, ...)      \
+    do {                                \
+        if (!(cond)) {                  \
+            ::ptgnn::set_error(__VA_ARGS__); \
+            return PTGNN_E_INVALID;     \
+        }                               \
+    } while (0)
+
+#define PTGNN_CUDA(call)                                                                          \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess) {                                                               \
+            ::ptgnn::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,               \
+                               cudaGetErrorString(err__));                                        \
+            return PTGNN_E_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+// Call right after a kernel launch: counts it and surfaces launch-configuration errors.
+#define PTGNN_LAUNCHED()                                   \
+    do {                                                   \
+        ::ptgnn::g_launch_count.fetch_add(1);              \
+        PTGNN_CUDA(cudaGetLastError());                    \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Bump allocator over a caller-provided workspace (256-byte aligned slices).
+struct Workspace {
+    char *base;
+    size_t size, used;
+    Workspace(void *p, size_t n) : base(static_cast<char *>(p)), size(n), used(0) {}
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        if (used + bytes > size) return nullptr;
+        T *r = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return r;
+    }
+};
+static inline size_t ws_slice(size_t count, size_t elt) { return align_up(count * elt, 256); }
+
+// ---- per-type edge tables passed by value as a kernel parameter (< 4 KB) -------------------------
+struct EdgeTables {
+    const int64_t *src[PTGNN_MAX_EDGE_TYPES];
+    const int64_t *tgt[PTGNN_MAX_EDGE_TYPES];
+    int64_t off[PTGNN_MAX_EDGE_TYPES + 1];
+    int num_types;
+};
+
+struct TypeOffsets {  // edge-id prefix offsets only (for kernels that need edge id -> type)
+    int32_t off[PTGNN_MAX_EDGE_TYPES + 1];
+    int num_types;
+};
+
+template <typename Off>
+__device__ __forceinline__ int type_of_edge(const Off *off, int num_types, int64_t e) {
+    // largest t with off[t] <= e  (empty types are skipped because off[t+1] == off[t] <= e moves on)
+    int lo = 0, hi = num_types - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)off[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---- device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes == 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {  // read-once data: do not allocate in L1
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float apply_act(float x, int kind) {
+    switch (kind) {
+        case PTGNN_ACT_GELU: return gelu_erf(x);
+        case PTGNN_ACT_TANH: return tanhf(x);
+        case PTGNN_ACT_RELU: return x > 0.0f ? x : 0.0f;
+        default: return x;
+    }
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace ptgnn

@@ -1,0 +1,175 @@
+"""``GraphNeuralNetwork`` container with the reference's API, owning the layer loop.
+
+Counterpart of `/root/reference/ptgnn/neuralmodels/gnn/graphneuralnetwork.py:28-209` (class ``GraphNeuralNetwork``)
+and the carrier types of `/root/reference/ptgnn/neuralmodels/gnn/structs.py:52-76`.  Differences that matter on B200:
+the container builds the edge plan once per minibatch and shares it with all of its layers (the reference rebuilds the
+equivalent grouping inside every ``scatter`` call), and it never mutates the caller's ``adjacency_lists`` list in place.
+Metric bookkeeping (``num_graphs/num_nodes/num_edges``, post-expansion edge count) is bit-identical.
+"""
+from typing import Any, Dict, List, NamedTuple, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .edgeplan import EdgePlan, plan_for
+from .messagepassing import AbstractMessagePassingLayer
+
+
+class GnnOutput(NamedTuple):
+    input_node_representations: torch.Tensor
+    output_node_representations: torch.Tensor
+    node_to_graph_idx: torch.Tensor
+    node_idx_references: Dict[str, torch.Tensor]
+    node_graph_idx_reference: Dict[str, torch.Tensor]
+    num_graphs: int
+
+    @property
+    def reference_nodes_idx(self) -> Dict[str, torch.Tensor]:
+        return self.node_idx_references
+
+    @property
+    def reference_nodes_graph_idx(self) -> Dict[str, torch.Tensor]:
+        return self.node_graph_idx_reference
+
+
+class GraphNeuralNetwork(nn.Module):
+    """Generic message-passing GNN over discrete edge types (duck-types the reference's ``ModuleWithMetrics``:
+    ``report_metrics`` / ``reset_metrics`` / ``_module_metrics`` / ``_reset_module_metrics``)."""
+
+    def __init__(
+        self,
+        message_passing_layers: List[AbstractMessagePassingLayer],
+        node_embedder: nn.Module,
+        introduce_backwards_edges: bool,
+        add_self_edges: bool,
+        edge_dropout_rate: float = 0.0,
+        edge_feature_embedder: Optional[nn.Module] = None,
+    ):
+        super().__init__()
+        assert 0 <= edge_dropout_rate < 1
+        self.__message_passing_layers = nn.ModuleList(message_passing_layers)
+        self.__node_embedder = node_embedder
+        self.__introduce_backwards_edges = introduce_backwards_edges
+        self.__add_self_edges = add_self_edges
+        self.__edge_dropout_rate = edge_dropout_rate
+        self.__edge_feature_embedder = edge_feature_embedder
+        self._reset_module_metrics()
+
+    # ---- metrics protocol (modulewithmetrics.py:8-77) ---------------------------------------------
+    def _reset_module_metrics(self) -> None:
+        self.__num_graphs, self.__num_edges, self.__num_nodes = 0, 0, 0
+
+    def _module_metrics(self) -> Dict[str, Any]:
+        return {"num_graphs": int(self.__num_graphs), "num_nodes": int(self.__num_nodes), "num_edges": int(self.__num_edges)}
+
+    def report_metrics(self) -> Dict[str, Any]:
+        metrics = self._module_metrics()
+        for child in self.modules():
+            if child is not self and hasattr(child, "_module_metrics"):
+                metrics.update(child._module_metrics())
+        return metrics
+
+    def reset_metrics(self) -> None:
+        for child in self.modules():
+            if hasattr(child, "_reset_module_metrics"):
+                child._reset_module_metrics()
+
+    def train(self, mode: bool = True):
+        self.reset_metrics()
+        return super().train(mode=mode)
+
+    def eval(self):
+        self.reset_metrics()
+        return super().eval()
+
+    # ---- properties ---------------------------------------------------------------------------------
+    @property
+    def input_node_state_dim(self) -> int:
+        return self.__message_passing_layers[0].input_state_dimension
+
+    @property
+    def output_node_state_dim(self) -> int:
+        return self.__message_passing_layers[-1].output_state_dimension
+
+    @property
+    def message_passing_layers(self) -> List[AbstractMessagePassingLayer]:
+        return self.__message_passing_layers
+
+    # ---- layer loop -----------------------------------------------------------------------------------
+    def gnn(
+        self,
+        node_representations: torch.Tensor,
+        adjacency_lists: List[Tuple[torch.Tensor, torch.Tensor]],
+        edge_feature_embeddings: List[torch.Tensor],
+        node_to_graph_idx: torch.Tensor,
+        reference_node_ids: Dict[str, torch.Tensor],
+        reference_node_graph_idx: Dict[str, torch.Tensor],
+        return_all_states: bool = False,
+        plan: Optional[EdgePlan] = None,
+    ) -> torch.Tensor:
+        if self.__edge_dropout_rate > 0 and self.training:
+            raise NotImplementedError("training-mode edge dropout has no native kernel (forward-only round)")
+        if node_representations.is_cuda:
+            plan = plan_for(adjacency_lists, node_representations.shape[0], plan)
+        previous = AbstractMessagePassingLayer._shared_plan
+        AbstractMessagePassingLayer._shared_plan = plan
+        try:
+            all_states = [node_representations]
+            for layer in self.__message_passing_layers:
+                node_representations = layer(
+                    node_states=node_representations,
+                    adjacency_lists=adjacency_lists,
+                    node_to_graph_idx=node_to_graph_idx,
+                    reference_node_ids=reference_node_ids,
+                    reference_node_graph_idx=reference_node_graph_idx,
+                    edge_features=edge_feature_embeddings,
+                )
+                all_states.append(node_representations)
+        finally:
+            AbstractMessagePassingLayer._shared_plan = previous
+        if return_all_states:
+            node_representations = torch.cat(all_states, dim=-1)
+        return node_representations
+
+    def expand_adjacency(self, adjacency_lists, num_nodes: int, device) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """Backward + self edge lists (graphneuralnetwork.py:172-186) as a NEW list."""
+        expanded = list(adjacency_lists)
+        if self.__introduce_backwards_edges:
+            expanded += [(tgt, src) for src, tgt in adjacency_lists]
+        if self.__add_self_edges:
+            ident = torch.arange(num_nodes, dtype=torch.int64, device=device)
+            expanded.append((ident, ident))
+        return expanded
+
+    def forward(
+        self,
+        *,
+        node_data,
+        adjacency_lists: List[Tuple[torch.Tensor, torch.Tensor]],
+        edge_feature_data: List,
+        node_to_graph_idx: torch.Tensor,
+        reference_node_ids: Dict[str, torch.Tensor],
+        reference_node_graph_idx: Dict[str, torch.Tensor],
+        num_graphs,
+        **kwargs,
+    ) -> GnnOutput:
+        initial = self.__node_embedder(**node_data)
+        device = node_to_graph_idx.device
+        num_nodes = node_to_graph_idx.shape[0]
+        if self.__edge_feature_embedder is not None:
+            raise NotImplementedError("edge feature embedders have no native kernel yet (SURVEY.md §8 row f-4)")
+        expanded = self.expand_adjacency(adjacency_lists, num_nodes, device)
+        edge_features = [torch.empty(src.shape[0], 0, device=device) for src, _ in expanded]
+        output = self.gnn(initial, expanded, edge_features, node_to_graph_idx, reference_node_ids,
+                          reference_node_graph_idx, **kwargs)
+        self.__num_edges += sum(src.shape[0] for src, _ in expanded)
+        self.__num_graphs += num_graphs
+        self.__num_nodes += num_nodes
+        return GnnOutput(
+            input_node_representations=initial,
+            output_node_representations=output,
+            node_to_graph_idx=node_to_graph_idx,
+            node_idx_references=reference_node_ids,
+            node_graph_idx_reference=reference_node_graph_idx,
+            num_graphs=num_graphs,
+        )

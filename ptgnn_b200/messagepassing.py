@@ -1,0 +1,350 @@
+"""Message-passing layers with the reference's ``nn.Module`` API, computed by the CUDA library.
+
+Drop-in for the classes the reference's factories construct
+(`/root/reference/ptgnn/implementations/typilus/train.py:39-99`, `ppi/train.py:36-57`, `varmisuse/train.py:42-107`):
+
+* ``AbstractMessagePassingLayer``  -- `/root/reference/ptgnn/neuralmodels/gnn/messagepassing/abstractmessagepassing.py:8-60`
+* ``GatedMessagePassingLayer``     -- `.../gatedmessagepassing.py:8-77`
+* ``MlpMessagePassingLayer``       -- `.../mlpmessagepassing.py:12-125`
+* ``MLP``                          -- `/root/reference/ptgnn/neuralmodels/mlp.py:9-80`
+
+Constructor signatures, properties, parameter initialisation order and (name-mangled) ``state_dict`` keys are the
+reference's, so reference checkpoints load with ``load_state_dict``.  ``forward`` never touches PyTorch arithmetic:
+it hands raw device pointers to ``libptgnn_b200.so``.  Configurations without a native kernel raise
+``NotImplementedError`` (there is no silent fallback): training-mode dropout, autograd, edge
+features (f-4), hidden message-MLP layers and module aggregators such as PNA (f-3).
+"""
+from abc import abstractmethod
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _native as N
+from .edgeplan import EdgePlan, plan_for
+
+_ACTIVATION_CODES = {type(None): N.ACT_NONE, nn.GELU: N.ACT_GELU, nn.Tanh: N.ACT_TANH, nn.ReLU: N.ACT_RELU}
+
+
+def _activation_code(module: Optional[nn.Module], what: str) -> int:
+    code = _ACTIVATION_CODES.get(type(module))
+    if code is None or (isinstance(module, nn.GELU) and getattr(module, "approximate", "none") != "none"):
+        raise NotImplementedError(f"{what}={module!r} has no native kernel (supported: GELU(erf), Tanh, ReLU, None)")
+    return code
+
+
+def _reduce_code(name) -> int:
+    if not isinstance(name, str) or name not in N.REDUCE:
+        raise NotImplementedError(f"message aggregation {name!r} has no native kernel (supported: sum, mean, max, min)")
+    return N.REDUCE[name]
+
+
+def _refuse_autograd(module: nn.Module, node_states: torch.Tensor) -> None:
+    if torch.is_grad_enabled() and (node_states.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise NotImplementedError(
+            "ptgnn_b200 layers are forward-only this round (backward = SURVEY.md §8 row f-1): call them under "
+            "torch.no_grad() / torch.inference_mode(), or set requires_grad_(False) on the parameters"
+        )
+
+
+def _check_no_edge_features(edge_features: Optional[List[torch.Tensor]]) -> None:
+    for f in edge_features or []:
+        if f is not None and f.dim() == 2 and f.shape[1] != 0:
+            raise NotImplementedError("edge features (F > 0) have no native kernel yet (SURVEY.md §8 row f-4)")
+
+
+class AbstractMessagePassingLayer(nn.Module):
+    """Interface of a message passing layer over multiple edge types (same contract as the reference's)."""
+
+    # A plan prepared by the container for the current minibatch (GraphNeuralNetwork.gnn sets/clears it);
+    # when absent the layer finds or builds the plan itself through the identity-keyed cache.
+    _shared_plan: Optional[EdgePlan] = None
+
+    @abstractmethod
+    def forward(
+        self,
+        node_states: torch.Tensor,
+        adjacency_lists: List[Tuple[torch.Tensor, torch.Tensor]],
+        node_to_graph_idx: torch.Tensor,
+        reference_node_ids: Dict[str, torch.Tensor],
+        reference_node_graph_idx: Dict[str, torch.Tensor],
+        edge_features: List[torch.Tensor],
+    ) -> torch.Tensor:
+        """[num_nodes, D] states + per-type (src, tgt) int64 lists -> [num_nodes, D'] states."""
+
+    def _aggregate_messages(self, messages: torch.Tensor, message_targets: torch.Tensor, num_nodes, aggregation_fn: str):
+        """Same contract as the reference helper: fp32 reduce, result cast back to the message dtype."""
+        from .scatter import scatter
+
+        return scatter(messages.to(torch.float32), message_targets, dim=0, dim_size=num_nodes, reduce=aggregation_fn).to(
+            messages.dtype
+        )
+
+    def _plan(self, adjacency_lists, num_nodes: int) -> EdgePlan:
+        return plan_for(adjacency_lists, num_nodes, AbstractMessagePassingLayer._shared_plan)
+
+    @property
+    @abstractmethod
+    def input_state_dimension(self) -> int:
+        pass
+
+    @property
+    @abstractmethod
+    def output_state_dimension(self) -> int:
+        pass
+
+
+class AbstractMessageAggregation(nn.Module):
+    @abstractmethod
+    def forward(self, messages: torch.Tensor, message_targets: torch.Tensor, num_nodes):
+        pass
+
+    @abstractmethod
+    def output_state_size(self, message_input_size: int) -> int:
+        pass
+
+
+class GatedMessagePassingLayer(AbstractMessagePassingLayer):
+    """GGNN layer:  m_e = W_t(e) h_src(e);  a_v = reduce m_e;  h'_v = GRUCell(a_v, h_v)."""
+
+    def __init__(
+        self,
+        state_dimension: int,
+        message_dimension: int,
+        num_edge_types: int,
+        message_aggregation_function: str,
+        dropout_rate: float = 0.0,
+        edge_feature_dimension: int = 0,
+    ):
+        super().__init__()
+        # construction + initialisation order follows the reference (gatedmessagepassing.py:20-35) so that the
+        # same torch seed yields the same parameters.
+        self.__edge_message_transformation_layers = nn.ModuleList(
+            nn.Linear(state_dimension + edge_feature_dimension, message_dimension, bias=False)
+            for _ in range(num_edge_types)
+        )
+        gain = (1 / num_edge_types) ** 0.5
+        for linear in self.__edge_message_transformation_layers:
+            nn.init.xavier_normal_(linear.weight, gain=gain)
+        self.__state_update = nn.GRUCell(input_size=message_dimension, hidden_size=state_dimension)
+        nn.init.orthogonal_(self.__state_update.weight_hh)
+        nn.init.xavier_uniform_(self.__state_update.weight_ih)
+        nn.init.normal_(self.__state_update.bias_hh, std=1e-5)
+        nn.init.normal_(self.__state_update.bias_ih, std=1e-5)
+        self.__state_dimension = state_dimension
+        self.__message_dimension = message_dimension
+        self.__edge_feature_dimension = edge_feature_dimension
+        self.__aggregation_fn = message_aggregation_function
+        self.__dropout = nn.Dropout(p=dropout_rate)
+
+    def forward(
+        self,
+        node_states: torch.Tensor,
+        adjacency_lists: List[Tuple[torch.Tensor, torch.Tensor]],
+        node_to_graph_idx: torch.Tensor = None,
+        reference_node_ids: Dict[str, torch.Tensor] = None,
+        reference_node_graph_idx: Dict[str, torch.Tensor] = None,
+        edge_features: List[torch.Tensor] = None,
+    ) -> torch.Tensor:
+        linears = self.__edge_message_transformation_layers
+        assert len(adjacency_lists) == len(linears), "one adjacency list per edge type is required"
+        if self.training and self.__dropout.p > 0:
+            raise NotImplementedError("training-mode dropout has no native kernel (forward-only round)")
+        if self.__edge_feature_dimension != 0:
+            raise NotImplementedError("edge features (F > 0) have no native kernel yet (SURVEY.md §8 row f-4)")
+        _check_no_edge_features(edge_features)
+        _refuse_autograd(self, node_states)
+        reduce = _reduce_code(self.__aggregation_fn)
+
+        h = N.require_cuda(node_states, "node_states", torch.float32)
+        num_nodes, H = h.shape
+        D = self.__message_dimension
+        plan = self._plan(adjacency_lists, num_nodes)
+        gru = self.__state_update
+        weights = [N.require_cuda(lin.weight, "edge weight", torch.float32) for lin in linears]
+        w_ih, w_hh = N.require_cuda(gru.weight_ih, "weight_ih", torch.float32), N.require_cuda(gru.weight_hh, "weight_hh", torch.float32)
+        b_ih, b_hh = N.require_cuda(gru.bias_ih, "bias_ih", torch.float32), N.require_cuda(gru.bias_hh, "bias_hh", torch.float32)
+
+        lib = N.lib()
+        ws_bytes = lib.ptgnn_b200_gated_workspace_bytes(num_nodes, plan.num_edges, H, D)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
+        out = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            rc = lib.ptgnn_b200_gated_forward_f32(
+                N.ptr(h), num_nodes, H, D, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
+                N.ptr(plan.src32), N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce,
+                N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+            )
+        N.check(rc, "ptgnn_b200_gated_forward_f32")
+        return out
+
+    @property
+    def input_state_dimension(self) -> int:
+        return self.__state_dimension
+
+    @property
+    def output_state_dimension(self) -> int:
+        return self.__state_dimension
+
+
+class MLP(nn.Module):
+    """Parameter container with the layout of the reference MLP (mlp.py:9-80): Sequential(Dropout, Linear,
+    [activation, Dropout, Linear]...), bias-free by default, no final activation.  Only the zero-hidden-layer
+    form (a single Linear) is executed natively, inside the edge-message kernel."""
+
+    def __init__(
+        self,
+        input_dimension: int,
+        output_dimension: int,
+        hidden_layers: Union[List[int], int] = 1,
+        use_biases: bool = False,
+        activation: Optional[nn.Module] = nn.ReLU(),
+        dropout_rate: float = 0.0,
+    ):
+        super().__init__()
+        if isinstance(hidden_layers, int):
+            width = 32 if output_dimension == 1 else output_dimension
+            hidden_sizes = [width] * hidden_layers
+        else:
+            hidden_sizes = list(hidden_layers)
+        assert len(hidden_sizes) <= 1 or activation is not None, "Multiple linear layers without an activation"
+        sizes = hidden_sizes + [output_dimension]
+        with_act: List[nn.Module] = []
+        fan_in = input_dimension
+        for i, size in enumerate(sizes):
+            linear = nn.Linear(fan_in, size, bias=use_biases)
+            nn.init.xavier_uniform_(linear.weight)
+            with_act += [nn.Dropout(p=dropout_rate), linear]
+            if i + 1 < len(sizes) and activation is not None:  # no activation after the output layer
+                with_act.append(activation)
+            fan_in = size
+        self.__mlp_modules = nn.Sequential(*with_act)
+        self.num_hidden_layers = len(hidden_sizes)
+        self.uses_biases = use_biases
+
+    @property
+    def single_linear(self) -> nn.Linear:
+        return self.__mlp_modules[1]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("MLP is executed inside the fused edge-message kernel, not as a stand-alone module")
+
+
+class MlpMessagePassingLayer(AbstractMessagePassingLayer):
+    """m_e = MLP_t([h_src ; h_tgt]);  a_v = reduce m_e;  h'_v = Dropout(act(W LN(GELU(a_v)) + b))."""
+
+    def __init__(
+        self,
+        input_state_dimension: int,
+        output_state_dimension: int,
+        message_dimension: int,
+        num_edge_types: int,
+        message_aggregation_function: Union[str, AbstractMessageAggregation],
+        message_activation: Optional[nn.Module] = nn.GELU(),
+        use_target_state_as_message_input: bool = True,
+        mlp_hidden_layers: Union[List[int], int] = 0,
+        use_layer_norm: bool = True,
+        use_dense_layer: bool = True,
+        dropout_rate: float = 0.0,
+        dense_activation: Optional[nn.Module] = nn.Tanh(),
+        features_dimension: int = 0,
+    ):
+        super().__init__()
+        self.__input_state_dim = input_state_dimension
+        self.__use_target_state_as_message_input = use_target_state_as_message_input
+        self.__output_state_dim = output_state_dimension
+        self.__message_dim = message_dimension
+        self.__features_dim = features_dimension
+        message_input = (2 if use_target_state_as_message_input else 1) * input_state_dimension
+        self.__edge_message_transformation_layers = nn.ModuleList(
+            MLP(input_dimension=message_input + features_dimension, output_dimension=message_dimension,
+                hidden_layers=mlp_hidden_layers)
+            for _ in range(num_edge_types)
+        )
+        self.__aggregation_fn = message_aggregation_function
+        if isinstance(message_aggregation_function, str):
+            aggregated_size = message_dimension
+        else:
+            aggregated_size = message_aggregation_function.output_state_size(message_dimension)
+        self.__aggregated_size = aggregated_size
+        self.__message_activation = message_activation
+
+        update: List[nn.Module] = []
+        if use_layer_norm:
+            update.append(nn.LayerNorm(aggregated_size))
+        if use_dense_layer:
+            update.append(nn.Linear(aggregated_size, output_state_dimension))
+            nn.init.xavier_uniform_(update[-1].weight)
+            if dense_activation is not None:
+                update.append(dense_activation)
+        update.append(nn.Dropout(p=dropout_rate))
+        self.__state_update = nn.Sequential(*update)
+
+    def forward(
+        self,
+        node_states: torch.Tensor,
+        adjacency_lists: List[Tuple[torch.Tensor, torch.Tensor]],
+        node_to_graph_idx: torch.Tensor = None,
+        reference_node_ids: Dict[str, torch.Tensor] = None,
+        reference_node_graph_idx: Dict[str, torch.Tensor] = None,
+        edge_features: List[torch.Tensor] = None,
+    ) -> torch.Tensor:
+        mlps = self.__edge_message_transformation_layers
+        assert len(adjacency_lists) == len(mlps), "The number of adjacency lists must be equal to the number of edge types."
+        if not isinstance(self.__aggregation_fn, str):
+            raise NotImplementedError("module aggregators (e.g. PnaMessageAggregation) have no native kernel yet (SURVEY.md §8 f-3)")
+        if any(m.num_hidden_layers != 0 or m.uses_biases for m in mlps):
+            raise NotImplementedError("message MLPs with hidden layers / biases have no native kernel yet")
+        if self.__features_dim != 0:
+            raise NotImplementedError("edge features (F > 0) have no native kernel yet (SURVEY.md §8 row f-4)")
+        _check_no_edge_features(edge_features)
+        _refuse_autograd(self, node_states)
+        reduce = _reduce_code(self.__aggregation_fn)
+        msg_act = _activation_code(self.__message_activation, "message_activation")
+
+        ln: Optional[nn.LayerNorm] = None
+        dense: Optional[nn.Linear] = None
+        dense_act = N.ACT_NONE
+        for m in self.__state_update:
+            if isinstance(m, nn.LayerNorm):
+                ln = m
+            elif isinstance(m, nn.Linear):
+                dense = m
+            elif isinstance(m, nn.Dropout):
+                if self.training and m.p > 0:
+                    raise NotImplementedError("training-mode dropout has no native kernel (forward-only round)")
+            else:
+                dense_act = _activation_code(m, "dense_activation")
+
+        h = N.require_cuda(node_states, "node_states", torch.float32)
+        num_nodes, H = h.shape
+        D = self.__message_dim
+        out_dim = dense.out_features if dense is not None else D
+        plan = self._plan(adjacency_lists, num_nodes)
+        weights = [N.require_cuda(m.single_linear.weight, "edge weight", torch.float32) for m in mlps]
+        f32 = lambda t, n: None if t is None else N.require_cuda(t, n, torch.float32)  # noqa: E731
+        ln_w, ln_b = (f32(ln.weight, "ln.weight"), f32(ln.bias, "ln.bias")) if ln is not None else (None, None)
+        d_w = f32(dense.weight, "dense.weight") if dense is not None else None
+        d_b = f32(dense.bias, "dense.bias") if dense is not None and dense.bias is not None else None
+
+        lib = N.lib()
+        ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes(num_nodes, plan.num_edges, H, D, out_dim)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
+        out = torch.empty(num_nodes, out_dim, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            rc = lib.ptgnn_b200_mlp_forward_f32(
+                N.ptr(h), num_nodes, H, D, out_dim, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
+                N.ptr(plan.src32), N.ptr(plan.tgt32), N.ptr_table(weights), int(self.__use_target_state_as_message_input),
+                reduce, msg_act, N.ptr(ln_w), N.ptr(ln_b), float(ln.eps) if ln is not None else 0.0, N.ptr(d_w), N.ptr(d_b),
+                dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+            )
+        N.check(rc, "ptgnn_b200_mlp_forward_f32")
+        return out
+
+    @property
+    def input_state_dimension(self) -> int:
+        return self.__input_state_dim
+
+    @property
+    def output_state_dimension(self) -> int:
+        return self.__output_state_dim

@@ -1,0 +1,103 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares, the
+module API mirrors the reference's, and the product refuses to run without CUDA (no CPU fallback)."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import ptgnn_b200 as P
+from ptgnn_b200 import _native as N
+from helpers import GOLDEN_MLP_KW, golden_state_dict, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ptgnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptgnn_b200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    handle = N.lib()
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/ptgnn_b200.h but not exported"
+    assert sorted(N.SIGNATURES) == declared, "ctypes SIGNATURES must cover exactly the header's entry points"
+    assert handle.ptgnn_b200_abi_version() == 1
+
+
+def test_workspace_size_queries_run_without_a_gpu():
+    handle = N.lib()
+    assert handle.ptgnn_b200_plan_workspace_bytes(1000, 5000) > 4 * 5000 * 4
+    assert handle.ptgnn_b200_gated_workspace_bytes(1000, 5000, 128, 128) >= 5000 * 128 * 4 + 1000 * 128 * 4
+    assert handle.ptgnn_b200_mlp_workspace_bytes(1000, 5000, 128, 128, 128) >= 5000 * 128 * 4
+    assert handle.ptgnn_b200_scatter_workspace_bytes(1000, 5000) > handle.ptgnn_b200_plan_workspace_bytes(1000, 5000)
+
+
+def test_no_cpu_fallback():
+    layer = P.GatedMessagePassingLayer(32, 32, 1, "sum").eval()
+    adj = [(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64))]
+    with torch.no_grad(), pytest.raises(N.NativeLibraryError):
+        layer(node_states=torch.zeros(4, 32), adjacency_lists=adj, node_to_graph_idx=None, reference_node_ids={},
+              reference_node_graph_idx={}, edge_features=[torch.empty(3, 0)])
+    with pytest.raises(N.NativeLibraryError):
+        P.scatter(torch.zeros(3, 4), torch.zeros(3, dtype=torch.int64), dim=0, dim_size=2, reduce="sum")
+
+
+def test_constructor_signatures_match_reference_contract():
+    gated = list(inspect.signature(P.GatedMessagePassingLayer.__init__).parameters)
+    assert gated == ["self", "state_dimension", "message_dimension", "num_edge_types", "message_aggregation_function",
+                     "dropout_rate", "edge_feature_dimension"]
+    mlp = list(inspect.signature(P.MlpMessagePassingLayer.__init__).parameters)
+    assert mlp == ["self", "input_state_dimension", "output_state_dimension", "message_dimension", "num_edge_types",
+                   "message_aggregation_function", "message_activation", "use_target_state_as_message_input",
+                   "mlp_hidden_layers", "use_layer_norm", "use_dense_layer", "dropout_rate", "dense_activation",
+                   "features_dimension"]
+    fwd = list(inspect.signature(P.AbstractMessagePassingLayer.forward).parameters)
+    assert fwd == ["self", "node_states", "adjacency_lists", "node_to_graph_idx", "reference_node_ids",
+                   "reference_node_graph_idx", "edge_features"]
+    gnn = list(inspect.signature(P.GraphNeuralNetwork.__init__).parameters)
+    assert gnn == ["self", "message_passing_layers", "node_embedder", "introduce_backwards_edges", "add_self_edges",
+                   "edge_dropout_rate", "edge_feature_embedder"]
+
+
+def test_reference_checkpoints_load():
+    g = load_golden("gated_sum")
+    layer = P.GatedMessagePassingLayer(32, 32, 4, "sum")
+    layer.load_state_dict(golden_state_dict(g), strict=True)
+    assert layer.input_state_dimension == 32 and layer.output_state_dimension == 32
+    for name, kw in GOLDEN_MLP_KW.items():
+        sd = golden_state_dict(load_golden(name))
+        T = sum(1 for k in sd if k.endswith("_MLP__mlp_modules.1.weight"))
+        P.MlpMessagePassingLayer(num_edge_types=T, **kw).load_state_dict(sd, strict=True)
+
+
+def test_unsupported_configurations_fail_loudly():
+    adj = [(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64))]
+    with pytest.raises(NotImplementedError):  # autograd
+        P.GatedMessagePassingLayer(32, 32, 1, "sum")(torch.zeros(4, 32), adj)
+    with torch.no_grad():
+        with pytest.raises(NotImplementedError):  # training-mode dropout
+            P.GatedMessagePassingLayer(32, 32, 1, "sum", dropout_rate=0.5).train()(torch.zeros(4, 32), adj)
+        with pytest.raises(NotImplementedError):  # hidden MLP layers
+            P.MlpMessagePassingLayer(32, 32, 32, 1, "sum", mlp_hidden_layers=1).eval()(torch.zeros(4, 32), adj)
+        with pytest.raises(NotImplementedError):  # unknown aggregation
+            P.GatedMessagePassingLayer(32, 32, 1, "median").eval()(torch.zeros(4, 32), adj)
+
+
+def test_container_metrics_protocol():
+    layer = P.GatedMessagePassingLayer(32, 32, 3, "sum")
+    gnn = P.GraphNeuralNetwork([layer, layer], torch.nn.Identity(), True, True)
+    assert gnn.report_metrics() == {"num_graphs": 0, "num_nodes": 0, "num_edges": 0}
+    assert gnn.input_node_state_dim == 32 and gnn.output_node_state_dim == 32
+    assert len(gnn.message_passing_layers) == 2
+    # weight sharing: the same module registered twice contributes its parameters once
+    assert len(list(gnn.parameters())) == len(list(layer.parameters()))
+    raw = [(torch.tensor([0, 1]), torch.tensor([1, 2]))]
+    expanded = gnn.expand_adjacency(raw, 4, torch.device("cpu"))
+    assert len(raw) == 1 and len(expanded) == 3  # caller's list is NOT mutated
+    assert torch.equal(expanded[1][0], raw[0][1]) and torch.equal(expanded[2][0], torch.arange(4))
