@@ -49,6 +49,21 @@ const char *ptgnn_b200_last_error(void);
 /* Number of kernel launches issued by this library in this process (bench.py's "gpu_launches"). */
 int64_t ptgnn_b200_launch_count(void);
 
+/* Optional per-kernel timing (bench.py's roofline leg): while enabled, every launch is bracketed by CUDA events
+ * on its own stream.  ptgnn_b200_kernel_timing_read synchronises, adds each category's elapsed milliseconds and
+ * launch count into ms[cat] / launches[cat] (cat < ncat) and clears the record. */
+enum {
+    PTGNN_KERNEL_PLAN = 0,    /* all edge-plan kernels */
+    PTGNN_KERNEL_MESSAGE = 1, /* edge_message_kernel */
+    PTGNN_KERNEL_REDUCE = 2,  /* segment_reduce_kernel */
+    PTGNN_KERNEL_GRU = 3,     /* gru_update_kernel */
+    PTGNN_KERNEL_DENSE = 4,   /* dense_update_kernel */
+    PTGNN_KERNEL_PACK = 5,    /* weight packing / conversion */
+    PTGNN_KERNEL_CATEGORIES = 6
+};
+int ptgnn_b200_kernel_timing_enable(int32_t enable);
+int ptgnn_b200_kernel_timing_read(double *ms /*[host]*/, int64_t *launches /*[host]*/, int32_t ncat);
+
 /* ------------------------------------------------------------------------------------------------
  * Edge plan -- replaces `torch.cat([adj[1] for adj in adjacency_lists])` (gatedmessagepassing.py:46,
  * mlpmessagepassing.py:102-109) and the index->row grouping inside torch_scatter.scatter: a canonical,

@@ -22,6 +22,8 @@ SIGNATURES = {
     "ptgnn_b200_abi_version": (ctypes.c_int, []),
     "ptgnn_b200_last_error": (ctypes.c_char_p, []),
     "ptgnn_b200_launch_count": (c_i64, []),
+    "ptgnn_b200_kernel_timing_enable": (ctypes.c_int, [c_i32]),
+    "ptgnn_b200_kernel_timing_read": (ctypes.c_int, [c_void_p, c_void_p, c_i32]),
     "ptgnn_b200_plan_workspace_bytes": (c_size_t, [c_i64, c_i64]),
     "ptgnn_b200_plan_build": (ctypes.c_int, [c_i64, c_i32, c_void_p, c_void_p, c_void_p] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_segment_reduce_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
@@ -74,6 +76,22 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().ptgnn_b200_launch_count())
+
+
+KERNEL_CATEGORIES = ("plan", "message", "reduce", "gru", "dense", "pack")
+
+
+def kernel_timing(enable: bool) -> None:
+    check(lib().ptgnn_b200_kernel_timing_enable(int(enable)), "kernel_timing_enable")
+
+
+def read_kernel_timing() -> dict:
+    """{category: (total_ms, launches)} accumulated since the last read (synchronises the device)."""
+    n = len(KERNEL_CATEGORIES)
+    ms = (ctypes.c_double * n)()
+    cnt = (c_i64 * n)()
+    check(lib().ptgnn_b200_kernel_timing_read(ms, cnt, n), "kernel_timing_read")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(KERNEL_CATEGORIES)}
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -1,6 +1,7 @@
 // C-ABI glue: error string, launch counter, and the host-buffer entry point used for end-to-end measurement.
 #include <stdarg.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -15,6 +16,25 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+}
+
+// ---- optional per-kernel timing ---------------------------------------------------------------------
+static std::atomic<int> g_timing_on{0};
+struct TimedRecord { int cat; cudaEvent_t a, b; };
+static std::mutex g_timing_mu;
+static std::vector<TimedRecord> g_timing_records;
+
+TimedScope::TimedScope(int category, cudaStream_t stream) : cat(category), st(stream) {
+    if (g_timing_on.load(std::memory_order_relaxed)) {
+        if (cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+    }
+}
+TimedScope::~TimedScope() {
+    if (a && b) {
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        g_timing_records.push_back({cat, a, b});
+    }
 }
 
 namespace {
@@ -34,6 +54,28 @@ using namespace ptgnn;
 extern "C" int ptgnn_b200_abi_version(void) { return PTGNN_B200_ABI_VERSION; }
 extern "C" const char *ptgnn_b200_last_error(void) { return g_error; }
 extern "C" int64_t ptgnn_b200_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int ptgnn_b200_kernel_timing_enable(int32_t enable) {
+    g_timing_on.store(enable ? 1 : 0);
+    return PTGNN_OK;
+}
+
+extern "C" int ptgnn_b200_kernel_timing_read(double *ms, int64_t *launches, int32_t ncat) {
+    PTGNN_CHECK_ARG(ms && launches && ncat > 0, "kernel_timing_read: bad arguments");
+    PTGNN_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (const TimedRecord &r : g_timing_records) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cat < ncat) {
+            ms[r.cat] += t;
+            launches[r.cat] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_timing_records.clear();
+    return PTGNN_OK;
+}
 
 // Mirrors GraphNeuralNetwork.gnn's layer loop (reference ptgnn/neuralmodels/gnn/graphneuralnetwork.py:121-131) for
 // a homogeneous stack of GatedMessagePassingLayers, from HOST buffers to HOST buffers.

@@ -32,6 +32,16 @@ extern std::atomic<int64_t> g_launch_count;
         }                                                                                         \
     } while (0)
 
+// RAII bracket around one kernel launch: when per-kernel timing is enabled (bench.py's roofline leg) it records a
+// CUDA event on the launch stream before and after; otherwise it costs one relaxed atomic load.
+struct TimedScope {
+    int cat;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    TimedScope(int category, cudaStream_t stream);
+    ~TimedScope();
+};
+
 // Call right after a kernel launch: counts it and surfaces launch-configuration errors.
 #define PTGNN_LAUNCHED()                                   \
     do {                                                   \

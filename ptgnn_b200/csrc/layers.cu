@@ -240,13 +240,19 @@ static int launch_edge_messages(const float *h, int H, int D, int use_target, in
         int rc = set_smem(edge_message_kernel<4>, Tile::SMEM_BYTES);
         if (rc) return rc;
         dim3 grid(tiles, (unsigned)ceil_div(D, Tile::BN));
-        edge_message_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h, H, use_target, D, src32, tgt32, pos, msg);
+        {
+            TimedScope timed__(PTGNN_KERNEL_MESSAGE, st);
+            edge_message_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h, H, use_target, D, src32, tgt32, pos, msg);
+        }
     } else {
         using Tile = GemmTile<8>;
         int rc = set_smem(edge_message_kernel<8>, Tile::SMEM_BYTES);
         if (rc) return rc;
         dim3 grid(tiles, (unsigned)ceil_div(D, Tile::BN));
-        edge_message_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h, H, use_target, D, src32, tgt32, pos, msg);
+        {
+            TimedScope timed__(PTGNN_KERNEL_MESSAGE, st);
+            edge_message_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h, H, use_target, D, src32, tgt32, pos, msg);
+        }
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
@@ -325,7 +331,10 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t nu
     float *msg = reinterpret_cast<float *>(ws + L.msg), *agg = reinterpret_cast<float *>(ws + L.agg);
     float *P1 = reinterpret_cast<float *>(ws + L.p1), *P2 = reinterpret_cast<float *>(ws + L.p2);
 
-    pack_gru_weights_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, P1, P2);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_gru_weights_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, P1, P2);
+    }
     PTGNN_LAUNCHED();
     rc = launch_edge_messages(node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg, st);
     if (rc) return rc;
@@ -335,8 +344,11 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t nu
     rc = set_smem(gru_update_kernel, Tile::SMEM_BYTES);
     if (rc) return rc;
     dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), H / 32);
-    gru_update_kernel<<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(agg, node_states, (int)num_nodes, H, D, P1, P2,
+    {
+        TimedScope timed__(PTGNN_KERNEL_GRU, st);
+        gru_update_kernel<<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(agg, node_states, (int)num_nodes, H, D, P1, P2,
                                                                      gru_b_ih, gru_b_hh, out_states);
+    }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
 }
@@ -394,17 +406,23 @@ extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_
             rc = set_smem(dense_update_kernel<4>, Tile::SMEM_BYTES);
             if (rc) return rc;
             dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
-            dense_update_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight,
+            {
+                TimedScope timed__(PTGNN_KERNEL_DENSE, st);
+                dense_update_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight,
                                                                                   dense_bias, out_dim, dense_activation,
                                                                                   out_states);
+            }
         } else {
             using Tile = GemmTile<8>;
             rc = set_smem(dense_update_kernel<8>, Tile::SMEM_BYTES);
             if (rc) return rc;
             dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
-            dense_update_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight,
+            {
+                TimedScope timed__(PTGNN_KERNEL_DENSE, st);
+                dense_update_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight,
                                                                                   dense_bias, out_dim, dense_activation,
                                                                                   out_states);
+            }
         }
         PTGNN_LAUNCHED();
     }

@@ -103,11 +103,20 @@ static int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int32_
                               cudaStream_t st) {
     if (n <= 0) return PTGNN_OK;
     const int64_t nb = ceil_div(n, SCAN_CHUNK);
-    scan_block_sums_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        scan_block_sums_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
+    }
     PTGNN_LAUNCHED();
-    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb);
+    }
     PTGNN_LAUNCHED();
-    scan_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums, out, out_total);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        scan_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums, out, out_total);
+    }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
 }
@@ -271,12 +280,18 @@ static int sort_edges_by_target(const int32_t *tgt32, int64_t N, int64_t E, int3
     for (int p = 0; p < passes; ++p) {
         int32_t *kout = keys[p & 1];
         int32_t *vout = (p == passes - 1) ? perm : vals[p & 1];
-        radix_hist_kernel<<<(unsigned)nblk, SORT_THREADS, 0, st>>>(kin, E, p * RADIX_BITS, hist);
+        {
+            TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+            radix_hist_kernel<<<(unsigned)nblk, SORT_THREADS, 0, st>>>(kin, E, p * RADIX_BITS, hist);
+        }
         PTGNN_LAUNCHED();
         int rc = exclusive_scan_i32(hist, hist, (int64_t)RADIX * nblk, hist_sums, nullptr, st);
         if (rc) return rc;
-        radix_scatter_kernel<<<(unsigned)nblk, SORT_THREADS, 0, st>>>(kin, vin, E, p * RADIX_BITS, p == 0, hist, kout,
+        {
+            TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+            radix_scatter_kernel<<<(unsigned)nblk, SORT_THREADS, 0, st>>>(kin, vin, E, p * RADIX_BITS, p == 0, hist, kout,
                                                                       vout);
+        }
         PTGNN_LAUNCHED();
         kin = kout;
         vin = vout;
@@ -339,14 +354,20 @@ extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int32_t num_types, const
     PTGNN_CHECK_ARG(num_nodes > 0, "plan_build: edges given but num_nodes == 0");
 
     const unsigned grid = (unsigned)(ceil_div(E, 256) < 148 * 16 ? ceil_div(E, 256) : 148 * 16);
-    convert_count_kernel<<<grid, 256, 0, st>>>(tabs, num_nodes, E, src32, tgt32, deg, status);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        convert_count_kernel<<<grid, 256, 0, st>>>(tabs, num_nodes, E, src32, tgt32, deg, status);
+    }
     PTGNN_LAUNCHED();
     // row_ptr[0..N] = exclusive scan of deg[0..N] (deg[N] == 0, so row_ptr[N] == E)
     int rc = exclusive_scan_i32(deg, row_ptr, num_nodes + 1, reinterpret_cast<int32_t *>(ws + L.scan_sums), nullptr, st);
     if (rc) return rc;
     rc = sort_edges_by_target(tgt32, num_nodes, E, perm, ws, L, st);
     if (rc) return rc;
-    finalize_plan_kernel<<<grid, 256, 0, st>>>(toff, E, perm, src32, pos, src_sorted, etype_sorted);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        finalize_plan_kernel<<<grid, 256, 0, st>>>(toff, E, perm, src32, pos, src_sorted, etype_sorted);
+    }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
 }

@@ -11,14 +11,23 @@ static int launch_shape(const float *msg, const int32_t *row_ptr, const int32_t 
     ReduceEpilogue e{};
     if (epi) e = *epi;
     if (epi) {
-        segment_reduce_kernel<RED, LPR, CHUNKS, false, true>
+        {
+            TimedScope timed__(PTGNN_KERNEL_REDUCE, st);
+            segment_reduce_kernel<RED, LPR, CHUNKS, false, true>
             <<<grid, 256, 0, st>>>(msg, row_ptr, perm, (int)N, (int)E, D, out, nullptr, e);
+        }
     } else if (arg_out && (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN)) {
-        segment_reduce_kernel<RED, LPR, CHUNKS, true, false>
+        {
+            TimedScope timed__(PTGNN_KERNEL_REDUCE, st);
+            segment_reduce_kernel<RED, LPR, CHUNKS, true, false>
             <<<grid, 256, 0, st>>>(msg, row_ptr, perm, (int)N, (int)E, D, out, arg_out, e);
+        }
     } else {
-        segment_reduce_kernel<RED, LPR, CHUNKS, false, false>
+        {
+            TimedScope timed__(PTGNN_KERNEL_REDUCE, st);
+            segment_reduce_kernel<RED, LPR, CHUNKS, false, false>
             <<<grid, 256, 0, st>>>(msg, row_ptr, perm, (int)N, (int)E, D, out, nullptr, e);
+        }
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;

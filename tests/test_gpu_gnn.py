@@ -55,7 +55,8 @@ def test_config1_ppi_shaped_batch():
     h = torch.randn(b.num_nodes, 64, generator=torch.Generator().manual_seed(0))
     out = _forward(gnn, h, b.adjacency_lists, num_graphs=b.num_graphs, node_to_graph=b.node_to_graph_idx)
     adj = O.expand_adjacency(b.adjacency_lists, b.num_nodes, True, True)
-    ref = O.gnn_forward(h, adj, [dict(kind="gated", aggregation_fn="sum", **gated_oracle_args(layer.state_dict()))])[-1]
+    sd = {k: v.cpu() for k, v in layer.state_dict().items()}
+    ref = O.gnn_forward(h, adj, [dict(kind="gated", aggregation_fn="sum", **gated_oracle_args(sd))])[-1]
     assert_close(out.output_node_representations.cpu(), ref, what="config 1")
     assert gnn.report_metrics() == {"num_graphs": 2, "num_nodes": 3000, "num_edges": 93000}
 
@@ -86,8 +87,9 @@ def test_config2_full_size_properties(agg):
     keep = torch.zeros(b.num_nodes, dtype=torch.bool)
     keep[rows] = True
     sub = [(s[keep[t]], t[keep[t]]) for s, t in adj]
+    sd = {k: v.cpu() for k, v in layer.state_dict().items()}
     ref = O.gated_layer_forward(h, sub, [torch.empty(a[0].shape[0], 0) for a in sub], aggregation_fn=agg,
-                                **gated_oracle_args(layer.state_dict()))
+                                **gated_oracle_args(sd))
     assert_close(out[rows], ref[rows], what=f"config 2 sampled rows ({agg})")
 
     # (b) edge order inside a type is irrelevant

@@ -56,7 +56,7 @@ def test_gated_vs_oracle_random(agg, n, H, counts):
     h = torch.randn(n, H, generator=gen)
     layer = P.GatedMessagePassingLayer(H, H, len(counts), agg)
     ref = O.gated_layer_forward(h, adj, [torch.empty(c, 0) for c in counts], aggregation_fn=agg,
-                                **gated_oracle_args(layer.state_dict()))
+                                **gated_oracle_args({k: v.clone() for k, v in layer.state_dict().items()}))
     assert_close(_run(layer, h, adj), ref, what=f"gated {agg} N={n} H={H}")
 
 
@@ -75,7 +75,7 @@ def test_mlp_vs_oracle_random(agg, n, Hin, D, Hout, counts):
     adj = random_adjacency(gen, n, counts)
     h = torch.randn(n, Hin, generator=gen)
     layer = P.MlpMessagePassingLayer(Hin, Hout, D, len(counts), agg)
-    sd = layer.state_dict()
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
     p = "_MlpMessagePassingLayer__"
     ref = O.mlp_layer_forward(
         h, adj, [torch.empty(c, 0) for c in counts],
