@@ -110,9 +110,12 @@ int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, int64_t num_e
  * edge_weights: [host] array of T device pointers, each nn.Linear.weight [D, H] row-major.
  * gru_*: nn.GRUCell parameters weight_ih [3H, D], weight_hh [3H, H], bias_ih/bias_hh [3H] (gate order r,z,n).
  * type_off: [host] T+1 prefix offsets of the per-type edge counts (edge-id space).
- * workspace >= ptgnn_b200_gated_workspace_bytes(...): message buffer [E, D] + aggregate [N, D] + packed GRU weights.
+ * workspace >= ptgnn_b200_gated_workspace_bytes(...): message buffer [E, D] + aggregate [N, D] + packed / TF32-split
+ * weights.  Dimensions that fit the tensor-core tiles (H % 32 == 0, D % 16 == 0) run on tcgen05 (3xTF32, fp32-exact);
+ * other multiples of 4 run on the FFMA kernels.  PTGNN_B200_DISABLE_TC=1 forces the FFMA kernels.
  * ---------------------------------------------------------------------------------------------- */
-size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t state_dim, int32_t message_dim);
+size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t state_dim,
+                                        int32_t message_dim);
 int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, int32_t state_dim, int32_t message_dim,
                                  int32_t num_types, const int64_t *type_off /*[host]*/, const int32_t *row_ptr,
                                  const int32_t *pos, const int32_t *src32,
@@ -127,8 +130,8 @@ int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, in
  * edge_weights[t]: [D, 2H] (or [D, H] when use_target_state == 0).  ln_weight/ln_bias NULL => no LayerNorm;
  * dense_weight NULL => no dense layer (output dim = D).  dense_weight [Hout, D], dense_bias [Hout].
  * ---------------------------------------------------------------------------------------------- */
-size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t in_dim, int32_t message_dim,
-                                      int32_t out_dim);
+size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t in_dim,
+                                      int32_t message_dim, int32_t out_dim, int32_t use_target_state);
 int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_nodes, int32_t in_dim, int32_t message_dim,
                                int32_t out_dim, int32_t num_types, const int64_t *type_off /*[host]*/,
                                const int32_t *row_ptr, const int32_t *pos, const int32_t *src32, const int32_t *tgt32,

@@ -122,7 +122,7 @@ extern "C" int ptgnn_b200_gated_gnn_forward_host_f32(const float *node_states, i
     int32_t *src32 = reinterpret_cast<int32_t *>(pb + sN + 3 * sE), *tgt32 = reinterpret_cast<int32_t *>(pb + sN + 4 * sE);
 
     const size_t ws_plan = ptgnn_b200_plan_workspace_bytes(num_nodes, E);
-    const size_t ws_layer = ptgnn_b200_gated_workspace_bytes(num_nodes, E, H, H);
+    const size_t ws_layer = ptgnn_b200_gated_workspace_bytes(num_nodes, E, num_types, H, H);
     const size_t ws_bytes = ws_plan > ws_layer ? ws_plan : ws_layer;
     PTGNN_CUDA(d_ws.alloc(ws_bytes));
     int rc = ptgnn_b200_plan_build(num_nodes, num_types, dsrc.data(), dtgt.data(), counts, row_ptr, perm, pos, src_sorted,

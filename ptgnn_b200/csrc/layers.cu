@@ -10,7 +10,10 @@
 //   2. segment_reduce_kernel (reduce.cuh) streaming CSR reduce = torch_scatter.scatter (+ GELU/LayerNorm for Mlp).
 //   3. gru_update_kernel     nn.GRUCell: both GEMMs ([agg;h] x packed gate weights) + gate math in one pass, or
 //      dense_update_kernel   Linear(+bias) + Tanh of the Mlp layer.
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
+#include "layers_tc.cuh"
 #include "reduce.cuh"
 
 namespace ptgnn {
@@ -265,8 +268,18 @@ static int check_layer_dims(const char *who, int64_t N, int64_t E, int H, int D)
     return PTGNN_OK;
 }
 
-struct GatedWs { size_t msg, agg, p1, p2, total; };
-static GatedWs gated_ws_layout(int64_t N, int64_t E, int H, int D) {
+// Tensor cores are the default; PTGNN_B200_DISABLE_TC=1 forces the FFMA kernels (A/B measurements, debugging).
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PTGNN_B200_DISABLE_TC");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+struct GatedWs { size_t msg, agg, p1, p2, wsplit, grupack, total; };
+static GatedWs gated_ws_layout(int64_t N, int64_t E, int T, int H, int D) {
     GatedWs w{};
     size_t o = 0;
     auto add = [&](size_t cnt) { size_t at = o; o += ws_slice(cnt, 4); return at; };
@@ -274,17 +287,21 @@ static GatedWs gated_ws_layout(int64_t N, int64_t E, int H, int D) {
     w.agg = add((size_t)N * D + 4);
     w.p1 = add((size_t)(H / 32 + 1) * 96 * D);
     w.p2 = add((size_t)(H / 32 + 1) * 96 * H);
+    w.wsplit = o; o += tc::split_edge_weights_bytes(T, D, H);
+    w.grupack = o; o += tc::gru_pack_bytes(H + 32, D);
     w.total = o;
     return w;
 }
 
-struct MlpWs { size_t msg, y, total; };
-static MlpWs mlp_ws_layout(int64_t N, int64_t E, int D) {
+struct MlpWs { size_t msg, y, wsplit, dsplit, total; };
+static MlpWs mlp_ws_layout(int64_t N, int64_t E, int T, int H, int D, int Hout, int use_target) {
     MlpWs w{};
     size_t o = 0;
     auto add = [&](size_t cnt) { size_t at = o; o += ws_slice(cnt, 4); return at; };
     w.msg = add((size_t)E * D + 4);
     w.y = add((size_t)N * D + 4);
+    w.wsplit = o; o += tc::split_edge_weights_bytes(T, D, use_target ? 2 * H : H);
+    w.dsplit = o; o += tc::dense_split_bytes(Hout > 0 ? Hout : D, D);
     w.total = o;
     return w;
 }
@@ -293,10 +310,10 @@ static MlpWs mlp_ws_layout(int64_t N, int64_t E, int D) {
 
 using namespace ptgnn;
 
-extern "C" size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t state_dim,
-                                                   int32_t message_dim) {
-    if (num_nodes < 0 || num_edges < 0 || state_dim <= 0 || message_dim <= 0) return 0;
-    return gated_ws_layout(num_nodes, num_edges, state_dim, message_dim).total;
+extern "C" size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types,
+                                                   int32_t state_dim, int32_t message_dim) {
+    if (num_nodes < 0 || num_edges < 0 || num_types < 0 || state_dim <= 0 || message_dim <= 0) return 0;
+    return gated_ws_layout(num_nodes, num_edges, num_types, state_dim, message_dim).total;
 }
 
 extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, int32_t state_dim,
@@ -322,7 +339,7 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t nu
     PTGNN_CHECK_ARG(node_states && out_states && row_ptr && gru_w_ih && gru_w_hh && gru_b_ih && gru_b_hh,
                     "gated_forward: null pointer");
     PTGNN_CHECK_ARG(E == 0 || (pos && src32 && edge_weights), "gated_forward: null edge arrays");
-    const GatedWs L = gated_ws_layout(num_nodes, E, H, D);
+    const GatedWs L = gated_ws_layout(num_nodes, E, num_types, H, D);
     if (workspace_bytes < L.total || !workspace) {
         set_error("gated_forward: workspace %zu < required %zu", workspace_bytes, L.total);
         return PTGNN_E_WORKSPACE;
@@ -331,15 +348,27 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t nu
     float *msg = reinterpret_cast<float *>(ws + L.msg), *agg = reinterpret_cast<float *>(ws + L.agg);
     float *P1 = reinterpret_cast<float *>(ws + L.p1), *P2 = reinterpret_cast<float *>(ws + L.p2);
 
+    // 1. per-edge messages, written at their target-sorted positions
+    if (tc_enabled() && tc::supported_message(H, D)) {
+        rc = tc::edge_messages(node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg,
+                               ws + L.wsplit, st);
+    } else {
+        rc = launch_edge_messages(node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg, st);
+    }
+    if (rc) return rc;
+    // 2. streaming segmented reduce
+    rc = launch_segment_reduce(msg, row_ptr, nullptr, num_nodes, E, D, reduce, agg, nullptr, nullptr, st);
+    if (rc) return rc;
+    // 3. GRUCell
+    if (tc_enabled() && tc::supported_gru(H, D)) {
+        return tc::gru_update(agg, node_states, num_nodes, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, out_states,
+                              ws + L.grupack, st);
+    }
     {
         TimedScope timed__(PTGNN_KERNEL_PACK, st);
         pack_gru_weights_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, P1, P2);
     }
     PTGNN_LAUNCHED();
-    rc = launch_edge_messages(node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg, st);
-    if (rc) return rc;
-    rc = launch_segment_reduce(msg, row_ptr, nullptr, num_nodes, E, D, reduce, agg, nullptr, nullptr, st);
-    if (rc) return rc;
     using Tile = GemmTile<6>;
     rc = set_smem(gru_update_kernel, Tile::SMEM_BYTES);
     if (rc) return rc;
@@ -353,11 +382,10 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t nu
     return PTGNN_OK;
 }
 
-extern "C" size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t in_dim,
-                                                 int32_t message_dim, int32_t out_dim) {
-    (void)in_dim; (void)out_dim;
-    if (num_nodes < 0 || num_edges < 0 || message_dim <= 0) return 0;
-    return mlp_ws_layout(num_nodes, num_edges, message_dim).total;
+extern "C" size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t in_dim,
+                                                 int32_t message_dim, int32_t out_dim, int32_t use_target_state) {
+    if (num_nodes < 0 || num_edges < 0 || num_types < 0 || in_dim <= 0 || message_dim <= 0) return 0;
+    return mlp_ws_layout(num_nodes, num_edges, num_types, in_dim, message_dim, out_dim, use_target_state).total;
 }
 
 extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_nodes, int32_t in_dim,
@@ -385,7 +413,7 @@ extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_
     PTGNN_CHECK_ARG(node_states && out_states && row_ptr, "mlp_forward: null pointer");
     PTGNN_CHECK_ARG(E == 0 || (pos && src32 && edge_weights && (!use_target_state || tgt32)),
                     "mlp_forward: null edge arrays");
-    const MlpWs L = mlp_ws_layout(num_nodes, E, D);
+    const MlpWs L = mlp_ws_layout(num_nodes, E, num_types, H, D, out_dim, use_target_state);
     if (workspace_bytes < L.total || !workspace) {
         set_error("mlp_forward: workspace %zu < required %zu", workspace_bytes, L.total);
         return PTGNN_E_WORKSPACE;
@@ -393,38 +421,44 @@ extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_
     char *ws = static_cast<char *>(workspace);
     float *msg = reinterpret_cast<float *>(ws + L.msg);
     float *y = dense_weight ? reinterpret_cast<float *>(ws + L.y) : out_states;
+    const int ut = use_target_state ? 1 : 0;
 
-    rc = launch_edge_messages(node_states, H, D, use_target_state ? 1 : 0, num_types, type_off, edge_weights, src32,
-                              tgt32, pos, msg, st);
+    if (tc_enabled() && tc::supported_message(H, D)) {
+        rc = tc::edge_messages(node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg,
+                               ws + L.wsplit, st);
+    } else {
+        rc = launch_edge_messages(node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg, st);
+    }
     if (rc) return rc;
     ReduceEpilogue epi{message_activation, ln_weight, ln_bias, ln_eps};
     rc = launch_segment_reduce(msg, row_ptr, nullptr, num_nodes, E, D, reduce, y, nullptr, &epi, st);
     if (rc) return rc;
-    if (dense_weight) {
-        if (out_dim <= 64) {
-            using Tile = GemmTile<4>;
-            rc = set_smem(dense_update_kernel<4>, Tile::SMEM_BYTES);
-            if (rc) return rc;
-            dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
-            {
-                TimedScope timed__(PTGNN_KERNEL_DENSE, st);
-                dense_update_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight,
-                                                                                  dense_bias, out_dim, dense_activation,
-                                                                                  out_states);
-            }
-        } else {
-            using Tile = GemmTile<8>;
-            rc = set_smem(dense_update_kernel<8>, Tile::SMEM_BYTES);
-            if (rc) return rc;
-            dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
-            {
-                TimedScope timed__(PTGNN_KERNEL_DENSE, st);
-                dense_update_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight,
-                                                                                  dense_bias, out_dim, dense_activation,
-                                                                                  out_states);
-            }
-        }
-        PTGNN_LAUNCHED();
+    if (!dense_weight) return PTGNN_OK;
+    if (tc_enabled() && tc::supported_dense(D, out_dim)) {
+        return tc::dense_update(y, num_nodes, D, dense_weight, dense_bias, out_dim, dense_activation, out_states,
+                                ws + L.dsplit, st);
     }
+    if (out_dim <= 64) {
+        using Tile = GemmTile<4>;
+        rc = set_smem(dense_update_kernel<4>, Tile::SMEM_BYTES);
+        if (rc) return rc;
+        dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
+        {
+            TimedScope timed__(PTGNN_KERNEL_DENSE, st);
+            dense_update_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight, dense_bias,
+                                                                                  out_dim, dense_activation, out_states);
+        }
+    } else {
+        using Tile = GemmTile<8>;
+        rc = set_smem(dense_update_kernel<8>, Tile::SMEM_BYTES);
+        if (rc) return rc;
+        dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
+        {
+            TimedScope timed__(PTGNN_KERNEL_DENSE, st);
+            dense_update_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight, dense_bias,
+                                                                                  out_dim, dense_activation, out_states);
+        }
+    }
+    PTGNN_LAUNCHED();
     return PTGNN_OK;
 }

@@ -1,0 +1,362 @@
+// Tensor-core (tcgen05, 3xTF32) versions of the three GEMM-bearing kernels of the hot path.  Same math and the same
+// reference lines as layers.cu (gatedmessagepassing.py:54-60,69; mlpmessagepassing.py:88-98,116); the pipeline is in
+// tc_pipeline.cuh, the policies below only say where rows come from and what the epilogue does with the tile.
+#include "layers_tc.cuh"
+
+#include "tc_pipeline.cuh"
+
+namespace ptgnn {
+namespace tc {
+
+// =================================================================================================
+// weight preparation: fp32 -> (hi, lo) TF32 pairs, optionally re-packed for the GRU gate blocks
+// =================================================================================================
+struct SplitSrc {
+    const float *w[PTGNN_MAX_EDGE_TYPES];
+    int num;
+    int elems;  // elements per matrix
+};
+__global__ void split_weights_kernel(const __grid_constant__ SplitSrc s, float *__restrict__ hi, float *__restrict__ lo) {
+    const int64_t total = (int64_t)s.num * s.elems;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = s.w[i / s.elems][i % s.elems];
+        const float h = tf32_hi(x);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+// P1[jb][n][k] = weight_ih[(n/32)*H + jb*32 + n%32][k], P2 likewise from weight_hh (n in [0,96): gates r, z, n)
+__global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh, int H, int D,
+                                      float *__restrict__ p1_hi, float *__restrict__ p1_lo, float *__restrict__ p2_hi,
+                                      float *__restrict__ p2_lo) {
+    const int nblk = H / 32;
+    const int64_t n1 = (int64_t)nblk * 96 * D, n2 = (int64_t)nblk * 96 * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
+        float x;
+        if (i < n1) {
+            const int k = (int)(i % D), n = (int)((i / D) % 96), jb = (int)(i / ((int64_t)96 * D));
+            x = w_ih[(size_t)((n / 32) * H + jb * 32 + n % 32) * D + k];
+            const float h = tf32_hi(x);
+            p1_hi[i] = h; p1_lo[i] = x - h;
+        } else {
+            const int64_t r = i - n1;
+            const int k = (int)(r % H), n = (int)((r / H) % 96), jb = (int)(r / ((int64_t)96 * H));
+            x = w_hh[(size_t)((n / 32) * H + jb * 32 + n % 32) * H + k];
+            const float h = tf32_hi(x);
+            p2_hi[r] = h; p2_lo[r] = x - h;
+        }
+    }
+}
+
+// =================================================================================================
+// policy 1: per-edge messages  (gather -> W_t -> row scattered to its target-sorted position)
+// =================================================================================================
+struct MsgPolicy {
+    struct Params {
+        const float *h;
+        const float *w_hi, *w_lo;     // [T][D][Kw]
+        const int32_t *src32, *tgt32, *pos;
+        float *msg;
+        int H, D, Kw, use_target, num_types, n_blocks;
+        int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
+        int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
+    };
+    struct Tile { int t, e0, e_end, n0, b_rows; };
+
+    __device__ static int num_tiles(const Params &p) { return p.tile_off[p.num_types] * p.n_blocks; }
+    __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
+        const int mt = tile / p.n_blocks, nb = tile % p.n_blocks;
+        int lo = 0, hi = p.num_types - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.tile_off[mid] <= mt) lo = mid; else hi = mid - 1;
+        }
+        ti.t = lo;
+        ti.e0 = p.edge_off[lo] + (mt - p.tile_off[lo]) * TILE_M;
+        ti.e_end = p.edge_off[lo + 1];
+        ti.n0 = nb * 128;
+        ti.b_rows = min(128, p.D - ti.n0);
+    }
+    __device__ static int num_segments(const Params &p, const Tile &) { return p.use_target ? 2 : 1; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
+        Segment s;
+        s.a = p.h; s.lda = p.H; s.K = p.H;
+        const size_t off = ((size_t)ti.t * p.D + ti.n0) * p.Kw + (size_t)seg * p.H;
+        s.b_hi = p.w_hi + off; s.b_lo = p.w_lo + off; s.ldb = p.Kw; s.b_rows = ti.b_rows;
+        return s;
+    }
+    __device__ static int gather_row(const Params &p, const Tile &ti, int seg, int r) {
+        const int e = ti.e0 + r;
+        if (e >= ti.e_end) return -1;
+        return seg == 0 ? p.src32[e] : p.tgt32[e];
+    }
+    __device__ static int mma_groups(const Params &, const Tile &ti, int seg, MmaGroup (&g)[2]) {
+        g[0] = MmaGroup{ti.b_rows, 0, 0, seg == 0};
+        return 1;
+    }
+    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane) {
+        const int e = ti.e0 + quarter * 32 + lane;
+        const bool ok = e < ti.e_end;
+        float *dst = p.msg;
+        if (ok) dst = p.msg + (size_t)p.pos[e] * p.D + ti.n0;
+        for (int c0 = 0; c0 < ti.b_rows; c0 += 32) {
+            if (ti.b_rows - c0 >= 32) {
+                float v[32];
+                tmem_ld_32cols(tmem_acc + c0, v);
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4 *>(dst + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            } else {  // 16-column tail (D % 32 == 16)
+                float v[16];
+                tmem_ld_16cols(tmem_acc + c0, v);
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4 *>(dst + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        }
+    }
+};
+
+// =================================================================================================
+// policy 2: nn.GRUCell update, 32 hidden units per tile:  columns [0,32) r | [32,64) z | [64,96) i_n | [96,128) h_n
+// =================================================================================================
+struct GruPolicy {
+    struct Params {
+        const float *agg, *h;
+        const float *p1_hi, *p1_lo, *p2_hi, *p2_lo;
+        const float *b_ih, *b_hh;
+        float *out;
+        int num_nodes, H, D, n_jb;
+    };
+    struct Tile { int row0, jb; };
+
+    __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_jb; }
+    __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
+        ti.row0 = (tile / p.n_jb) * TILE_M;   // jb fastest: the CTAs that share a row tile run at the same time (L2 reuse)
+        ti.jb = tile % p.n_jb;
+    }
+    __device__ static int num_segments(const Params &, const Tile &) { return 2; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
+        Segment s;
+        if (seg == 0) {
+            s.a = p.agg; s.lda = p.D; s.K = p.D;
+            s.b_hi = p.p1_hi + (size_t)ti.jb * 96 * p.D; s.b_lo = p.p1_lo + (size_t)ti.jb * 96 * p.D; s.ldb = p.D;
+        } else {
+            s.a = p.h; s.lda = p.H; s.K = p.H;
+            s.b_hi = p.p2_hi + (size_t)ti.jb * 96 * p.H; s.b_lo = p.p2_lo + (size_t)ti.jb * 96 * p.H; s.ldb = p.H;
+        }
+        s.b_rows = 96;
+        return s;
+    }
+    __device__ static int gather_row(const Params &p, const Tile &ti, int, int r) {
+        const int row = ti.row0 + r;
+        return row < p.num_nodes ? row : -1;
+    }
+    __device__ static int mma_groups(const Params &, const Tile &, int seg, MmaGroup (&g)[2]) {
+        if (seg == 0) {  // [r z i_n] = agg x W_i{r,z,n}^T
+            g[0] = MmaGroup{96, 0, 0, true};
+            return 1;
+        }
+        g[0] = MmaGroup{64, 0, 0, false};   // [r z] += h x W_h{r,z}^T
+        g[1] = MmaGroup{32, 64, 96, true};  // h_n   = h x W_hn^T
+        return 2;
+    }
+    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane) {
+        const int row = ti.row0 + quarter * 32 + lane;
+        const bool ok = row < p.num_nodes;
+        const int H = p.H;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float r[16], z[16], gin[16], ghn[16];
+            tmem_ld_16cols(tmem_acc + 16 * half, r);
+            tmem_ld_16cols(tmem_acc + 32 + 16 * half, z);
+            tmem_ld_16cols(tmem_acc + 64 + 16 * half, gin);
+            tmem_ld_16cols(tmem_acc + 96 + 16 * half, ghn);
+            if (ok) {
+                const int j0 = ti.jb * 32 + 16 * half;
+                const float *hrow = p.h + (size_t)row * H + j0;
+                float *orow = p.out + (size_t)row * H + j0;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 hv = *reinterpret_cast<const float4 *>(hrow + 4 * i4);
+                    const float hval[4] = {hv.x, hv.y, hv.z, hv.w};
+                    float o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = 4 * i4 + u, j = j0 + i;
+                        const float rr = sigmoid_f(r[i] + (p.b_ih[j] + p.b_hh[j]));
+                        const float zz = sigmoid_f(z[i] + (p.b_ih[H + j] + p.b_hh[H + j]));
+                        const float nn = tanhf(gin[i] + p.b_ih[2 * H + j] + rr * (ghn[i] + p.b_hh[2 * H + j]));
+                        o[u] = (1.0f - zz) * nn + zz * hval[u];
+                    }
+                    *reinterpret_cast<float4 *>(orow + 4 * i4) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+};
+
+// =================================================================================================
+// policy 3: Mlp dense update   out = act(y W^T + b)
+// =================================================================================================
+struct DensePolicy {
+    struct Params {
+        const float *y;
+        const float *w_hi, *w_lo;   // [Hout][D]
+        const float *bias;
+        float *out;
+        int num_nodes, D, Hout, act, n_blocks;
+    };
+    struct Tile { int row0, n0, b_rows; };
+
+    __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_blocks; }
+    __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
+        ti.row0 = (tile / p.n_blocks) * TILE_M;
+        ti.n0 = (tile % p.n_blocks) * 128;
+        ti.b_rows = min(128, p.Hout - ti.n0);
+    }
+    __device__ static int num_segments(const Params &, const Tile &) { return 1; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int) {
+        Segment s;
+        s.a = p.y; s.lda = p.D; s.K = p.D;
+        s.b_hi = p.w_hi + (size_t)ti.n0 * p.D; s.b_lo = p.w_lo + (size_t)ti.n0 * p.D; s.ldb = p.D; s.b_rows = ti.b_rows;
+        return s;
+    }
+    __device__ static int gather_row(const Params &p, const Tile &ti, int, int r) {
+        const int row = ti.row0 + r;
+        return row < p.num_nodes ? row : -1;
+    }
+    __device__ static int mma_groups(const Params &, const Tile &ti, int, MmaGroup (&g)[2]) {
+        g[0] = MmaGroup{ti.b_rows, 0, 0, true};
+        return 1;
+    }
+    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane) {
+        const int row = ti.row0 + quarter * 32 + lane;
+        const bool ok = row < p.num_nodes;
+        for (int c0 = 0; c0 < ti.b_rows; c0 += 16) {
+            float v[16];
+            tmem_ld_16cols(tmem_acc + c0, v);
+            if (ok) {
+                float *orow = p.out + (size_t)row * p.Hout + ti.n0 + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float b = p.bias ? p.bias[ti.n0 + c0 + i + u] : 0.0f;
+                        o[u] = apply_act(v[i + u] + b, p.act);
+                    }
+                    *reinterpret_cast<float4 *>(orow + i) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+};
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <class Policy>
+static int launch_pipeline(const typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
+    if (total_tiles <= 0) return PTGNN_OK;
+    static bool configured = false;
+    if (!configured) {
+        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    {
+        TimedScope timed__(category, st);
+        tc_pipeline_kernel<Policy><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+size_t split_edge_weights_bytes(int num_types, int D, int Kw) { return 2 * ws_slice((size_t)num_types * D * Kw, 4); }
+size_t gru_pack_bytes(int H, int D) { return 2 * ws_slice((size_t)(H / 32) * 96 * D, 4) + 2 * ws_slice((size_t)(H / 32) * 96 * H, 4); }
+size_t dense_split_bytes(int Hout, int D) { return 2 * ws_slice((size_t)Hout * D, 4); }
+
+bool supported_message(int H, int D) { return H % 4 == 0 && D % 16 == 0 && H >= 8 && D >= 16; }
+bool supported_gru(int H, int D) { return H % 32 == 0 && D % 4 == 0 && D >= 8; }
+bool supported_dense(int D, int Hout) { return D % 4 == 0 && Hout % 16 == 0 && D >= 8; }
+
+int edge_messages(const float *h, int H, int D, int use_target, int num_types, const int64_t *type_off,
+                  const float *const *weights, const int32_t *src32, const int32_t *tgt32, const int32_t *pos, float *msg,
+                  void *scratch, cudaStream_t st) {
+    const int Kw = use_target ? 2 * H : H;
+    float *w_hi = static_cast<float *>(scratch);
+    float *w_lo = reinterpret_cast<float *>(static_cast<char *>(scratch) + ws_slice((size_t)num_types * D * Kw, 4));
+    SplitSrc ss{};
+    ss.num = num_types; ss.elems = D * Kw;
+    for (int t = 0; t < num_types; ++t) ss.w[t] = weights[t];
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        split_weights_kernel<<<148, 256, 0, st>>>(ss, w_hi, w_lo);
+    }
+    PTGNN_LAUNCHED();
+
+    MsgPolicy::Params p{};
+    p.h = h; p.w_hi = w_hi; p.w_lo = w_lo; p.src32 = src32; p.tgt32 = tgt32; p.pos = pos; p.msg = msg;
+    p.H = H; p.D = D; p.Kw = Kw; p.use_target = use_target; p.num_types = num_types; p.n_blocks = (D + 127) / 128;
+    int tiles = 0;
+    for (int t = 0; t < num_types; ++t) {
+        p.edge_off[t] = (int32_t)type_off[t];
+        p.tile_off[t] = tiles;
+        tiles += (int)ceil_div(type_off[t + 1] - type_off[t], TILE_M);
+    }
+    for (int t = num_types; t <= PTGNN_MAX_EDGE_TYPES; ++t) { p.edge_off[t] = (int32_t)type_off[num_types]; p.tile_off[t] = tiles; }
+    return launch_pipeline<MsgPolicy>(p, tiles * p.n_blocks, PTGNN_KERNEL_MESSAGE, st);
+}
+
+int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D, const float *w_ih, const float *w_hh,
+               const float *b_ih, const float *b_hh, float *out, void *scratch, cudaStream_t st) {
+    char *s = static_cast<char *>(scratch);
+    const size_t s1 = ws_slice((size_t)(H / 32) * 96 * D, 4), s2 = ws_slice((size_t)(H / 32) * 96 * H, 4);
+    float *p1_hi = reinterpret_cast<float *>(s), *p1_lo = reinterpret_cast<float *>(s + s1);
+    float *p2_hi = reinterpret_cast<float *>(s + 2 * s1), *p2_lo = reinterpret_cast<float *>(s + 2 * s1 + s2);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_split_gru_kernel<<<148, 256, 0, st>>>(w_ih, w_hh, H, D, p1_hi, p1_lo, p2_hi, p2_lo);
+    }
+    PTGNN_LAUNCHED();
+    GruPolicy::Params p{};
+    p.agg = agg; p.h = h; p.p1_hi = p1_hi; p.p1_lo = p1_lo; p.p2_hi = p2_hi; p.p2_lo = p2_lo; p.b_ih = b_ih; p.b_hh = b_hh;
+    p.out = out; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = H / 32;
+    const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_jb;
+    return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, st);
+}
+
+int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const float *bias, int Hout, int act, float *out,
+                 void *scratch, cudaStream_t st) {
+    float *w_hi = static_cast<float *>(scratch);
+    float *w_lo = reinterpret_cast<float *>(static_cast<char *>(scratch) + ws_slice((size_t)Hout * D, 4));
+    SplitSrc ss{};
+    ss.num = 1; ss.elems = Hout * D; ss.w[0] = W;
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        split_weights_kernel<<<148, 256, 0, st>>>(ss, w_hi, w_lo);
+    }
+    PTGNN_LAUNCHED();
+    DensePolicy::Params p{};
+    p.y = y; p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.out = out; p.num_nodes = (int)num_nodes; p.D = D; p.Hout = Hout;
+    p.act = act; p.n_blocks = (Hout + 127) / 128;
+    const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_blocks;
+    return launch_pipeline<DensePolicy>(p, tiles, PTGNN_KERNEL_DENSE, st);
+}
+
+}  // namespace tc
+}  // namespace ptgnn

@@ -1,0 +1,28 @@
+// Entry points of the tensor-core (tcgen05, 3xTF32) kernels; see layers_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ptgnn {
+namespace tc {
+
+bool supported_message(int H, int D);
+bool supported_gru(int H, int D);
+bool supported_dense(int D, int Hout);
+
+size_t split_edge_weights_bytes(int num_types, int D, int Kw);
+size_t gru_pack_bytes(int H, int D);
+size_t dense_split_bytes(int Hout, int D);
+
+// messages[pos[e]] = W_t(e) [h_src(e) ; h_tgt(e)]          (scratch >= split_edge_weights_bytes)
+int edge_messages(const float *h, int H, int D, int use_target, int num_types, const int64_t *type_off,
+                  const float *const *weights, const int32_t *src32, const int32_t *tgt32, const int32_t *pos, float *msg,
+                  void *scratch, cudaStream_t st);
+// out = GRUCell(agg, h)                                     (scratch >= gru_pack_bytes)
+int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D, const float *w_ih, const float *w_hh,
+               const float *b_ih, const float *b_hh, float *out, void *scratch, cudaStream_t st);
+// out = act(y W^T + b)                                      (scratch >= dense_split_bytes)
+int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const float *bias, int Hout, int act, float *out,
+                 void *scratch, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace ptgnn

@@ -1,0 +1,133 @@
+// Blackwell (sm_100a) tensor-core plumbing for the fp32-exact GEMMs of the hot path: tcgen05.mma (kind::tf32, fp32
+// accumulate in TMEM), mbarrier pipelines, TMEM allocation and readback.  Hand-written inline PTX; no CUTLASS.
+//
+// fp32 accuracy on TF32 tensor cores ("3xTF32"): every fp32 operand x is split as x = hi + lo with
+// hi = x with the low 13 mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32,
+// <= 13 significant bits).  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi; the dropped a_lo*b_lo term and the TF32
+// truncation of the lo parts are both O(2^-22) relative, i.e. fp32-rounding level, which is what keeps the layer
+// inside the north_star's 1e-5 tolerance (a single TF32 product would be ~1e-3).
+//
+// Shared-memory operand layout (both A and B are K-major, rows of 32 fp32 = 128 bytes): the canonical
+// SWIZZLE_128B K-major layout -- 8-row groups of 1024 bytes, 16-byte chunk index XOR (row & 7).  One tcgen05.mma
+// consumes K = 8 fp32 (32 bytes) per instruction; advancing K inside the 128-byte row is a +32-byte bump of the
+// descriptor's start address.
+#pragma once
+#include "common.cuh"
+
+namespace ptgnn {
+namespace tc {
+
+// ---- mbarrier -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 21); ++spin) {  // ~1 us suspend hint per try => bounded at a few seconds
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// ---- proxy / tcgen05 fences ---------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp executes these) ---------------------------------------------------
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result) {
+    static_assert(COLS == 32 || COLS == 64 || COLS == 128 || COLS == 256 || COLS == 512, "TMEM columns: power of 2 >= 32");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address (>>4) bits [0,14), LBO bits [16,30) = 0
+// (single swizzle atom along K), SBO bits [32,46) = 1024 >> 4 (8-row group pitch), version bits [46,48) = 1 (sm_100),
+// layout type bits [61,64) = 2 (SWIZZLE_128B).  The tile base must be 1024-byte aligned (base_offset = 0).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (upper 32 bits of the idesc operand): D = F32 (bits [4,6) = 1), A/B format bits [7,10) /
+// [10,13) (0 = F16, 1 = BF16, 2 = TF32), both K-major (bits 15, 16 = 0), N >> 3 at bits [17,23), M >> 4 at bits [24,29).
+__host__ __device__ constexpr uint32_t make_instr_desc(uint32_t ab_format, uint32_t M, uint32_t N) {
+    return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+constexpr uint32_t FMT_BF16 = 1, FMT_TF32 = 2;
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; one elected thread issues.
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: warp w reads its 32-lane quarter (lanes 32*(w%4)..), 32 consecutive fp32 columns ------
+__device__ __forceinline__ void tmem_ld_32cols(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld_16cols(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- 3xTF32 operand split -----------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+}  // namespace tc
+}  // namespace ptgnn

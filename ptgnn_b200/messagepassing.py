@@ -166,7 +166,7 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         b_ih, b_hh = N.require_cuda(gru.bias_ih, "bias_ih", torch.float32), N.require_cuda(gru.bias_hh, "bias_hh", torch.float32)
 
         lib = N.lib()
-        ws_bytes = lib.ptgnn_b200_gated_workspace_bytes(num_nodes, plan.num_edges, H, D)
+        ws_bytes = lib.ptgnn_b200_gated_workspace_bytes(num_nodes, plan.num_edges, plan.num_types, H, D)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
         out = torch.empty_like(h)
         with torch.cuda.device(h.device):
@@ -328,7 +328,8 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         d_b = f32(dense.bias, "dense.bias") if dense is not None and dense.bias is not None else None
 
         lib = N.lib()
-        ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes(num_nodes, plan.num_edges, H, D, out_dim)
+        ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes(
+            num_nodes, plan.num_edges, plan.num_types, H, D, out_dim, int(self.__use_target_state_as_message_input))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
         out = torch.empty(num_nodes, out_dim, dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):

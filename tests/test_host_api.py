@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_workspace_size_queries_run_without_a_gpu():
     handle = N.lib()
     assert handle.ptgnn_b200_plan_workspace_bytes(1000, 5000) > 4 * 5000 * 4
-    assert handle.ptgnn_b200_gated_workspace_bytes(1000, 5000, 128, 128) >= 5000 * 128 * 4 + 1000 * 128 * 4
-    assert handle.ptgnn_b200_mlp_workspace_bytes(1000, 5000, 128, 128, 128) >= 5000 * 128 * 4
+    assert handle.ptgnn_b200_gated_workspace_bytes(1000, 5000, 17, 128, 128) >= 5000 * 128 * 4 + 1000 * 128 * 4
+    assert handle.ptgnn_b200_mlp_workspace_bytes(1000, 5000, 17, 128, 128, 128, 1) >= 5000 * 128 * 4
     assert handle.ptgnn_b200_scatter_workspace_bytes(1000, 5000) > handle.ptgnn_b200_plan_workspace_bytes(1000, 5000)
 
 
