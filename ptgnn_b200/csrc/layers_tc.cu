@@ -9,6 +9,40 @@ namespace ptgnn {
 namespace tc {
 
 // =================================================================================================
+// TMA tensor maps (driver entry point fetched through the runtime: no libcuda link dependency)
+// =================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+// fp32 row-major [rows, cols] (row pitch = pitch_elems), box = {32 columns (128 bytes), box_rows}, SWIZZLE_128B;
+// out-of-bounds elements are zero-filled.
+static int make_map_2d(CUtensorMap *map, const float *base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                       uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return PTGNN_E_CUDA; }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)CHUNK_K, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PTGNN_E_CUDA; }
+    return PTGNN_OK;
+}
+
+// =================================================================================================
 // weight preparation: fp32 -> (hi, lo) TF32 pairs, optionally re-packed for the GRU gate blocks
 // =================================================================================================
 struct SplitSrc {
@@ -53,8 +87,8 @@ __global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const floa
 // =================================================================================================
 struct MsgPolicy {
     struct Params {
+        CUtensorMap map_w_hi, map_w_lo;   // [T*D, Kw], box {32, min(128, D)}
         const float *h;
-        const float *w_hi, *w_lo;     // [T][D][Kw]
         const int32_t *src32, *tgt32, *pos;
         float *msg;
         int H, D, Kw, use_target, num_types, n_blocks;
@@ -80,9 +114,9 @@ struct MsgPolicy {
     __device__ static int num_segments(const Params &p, const Tile &) { return p.use_target ? 2 : 1; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
         Segment s;
-        s.a = p.h; s.lda = p.H; s.K = p.H;
-        const size_t off = ((size_t)ti.t * p.D + ti.n0) * p.Kw + (size_t)seg * p.H;
-        s.b_hi = p.w_hi + off; s.b_lo = p.w_lo + off; s.ldb = p.Kw; s.b_rows = ti.b_rows;
+        s.a = p.h; s.lda = p.H; s.K = p.H; s.a_map = nullptr; s.a_row0 = 0;
+        s.b_hi_map = &p.map_w_hi; s.b_lo_map = &p.map_w_lo;
+        s.b_row0 = ti.t * p.D + ti.n0; s.b_col0 = seg * p.H; s.b_box_rows = min(128, p.D);
         return s;
     }
     __device__ static int gather_row(const Params &p, const Tile &ti, int seg, int r) {
@@ -102,7 +136,7 @@ struct MsgPolicy {
         for (int c0 = 0; c0 < ti.b_rows; c0 += 32) {
             if (ti.b_rows - c0 >= 32) {
                 float v[32];
-                tmem_ld_32cols(tmem_acc + c0, v);
+                tmem_ld_acc32(tmem_acc + c0, v);
                 if (ok) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
@@ -110,7 +144,7 @@ struct MsgPolicy {
                 }
             } else {  // 16-column tail (D % 32 == 16)
                 float v[16];
-                tmem_ld_16cols(tmem_acc + c0, v);
+                tmem_ld_acc16(tmem_acc + c0, v);
                 if (ok) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -126,8 +160,9 @@ struct MsgPolicy {
 // =================================================================================================
 struct GruPolicy {
     struct Params {
-        const float *agg, *h;
-        const float *p1_hi, *p1_lo, *p2_hi, *p2_lo;
+        CUtensorMap map_agg, map_h;                              // [N, D], [N, H], box {32, 128}
+        CUtensorMap map_p1_hi, map_p1_lo, map_p2_hi, map_p2_lo;  // [n_jb*96, D] / [n_jb*96, H], box {32, 96}
+        const float *h;
         const float *b_ih, *b_hh;
         float *out;
         int num_nodes, H, D, n_jb;
@@ -142,14 +177,12 @@ struct GruPolicy {
     __device__ static int num_segments(const Params &, const Tile &) { return 2; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
         Segment s;
+        s.a = nullptr; s.lda = 0; s.a_row0 = ti.row0; s.b_row0 = ti.jb * 96; s.b_col0 = 0; s.b_box_rows = 96;
         if (seg == 0) {
-            s.a = p.agg; s.lda = p.D; s.K = p.D;
-            s.b_hi = p.p1_hi + (size_t)ti.jb * 96 * p.D; s.b_lo = p.p1_lo + (size_t)ti.jb * 96 * p.D; s.ldb = p.D;
+            s.a_map = &p.map_agg; s.K = p.D; s.b_hi_map = &p.map_p1_hi; s.b_lo_map = &p.map_p1_lo;
         } else {
-            s.a = p.h; s.lda = p.H; s.K = p.H;
-            s.b_hi = p.p2_hi + (size_t)ti.jb * 96 * p.H; s.b_lo = p.p2_lo + (size_t)ti.jb * 96 * p.H; s.ldb = p.H;
+            s.a_map = &p.map_h; s.K = p.H; s.b_hi_map = &p.map_p2_hi; s.b_lo_map = &p.map_p2_lo;
         }
-        s.b_rows = 96;
         return s;
     }
     __device__ static int gather_row(const Params &p, const Tile &ti, int, int r) {
@@ -172,10 +205,10 @@ struct GruPolicy {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float r[16], z[16], gin[16], ghn[16];
-            tmem_ld_16cols(tmem_acc + 16 * half, r);
-            tmem_ld_16cols(tmem_acc + 32 + 16 * half, z);
-            tmem_ld_16cols(tmem_acc + 64 + 16 * half, gin);
-            tmem_ld_16cols(tmem_acc + 96 + 16 * half, ghn);
+            tmem_ld_acc16(tmem_acc + 16 * half, r);
+            tmem_ld_acc16(tmem_acc + 32 + 16 * half, z);
+            tmem_ld_acc16(tmem_acc + 64 + 16 * half, gin);
+            tmem_ld_acc16(tmem_acc + 96 + 16 * half, ghn);
             if (ok) {
                 const int j0 = ti.jb * 32 + 16 * half;
                 const float *hrow = p.h + (size_t)row * H + j0;
@@ -205,8 +238,7 @@ struct GruPolicy {
 // =================================================================================================
 struct DensePolicy {
     struct Params {
-        const float *y;
-        const float *w_hi, *w_lo;   // [Hout][D]
+        CUtensorMap map_y, map_w_hi, map_w_lo;   // [N, D] box {32,128}; [Hout, D] box {32, min(128, Hout)}
         const float *bias;
         float *out;
         int num_nodes, D, Hout, act, n_blocks;
@@ -222,8 +254,8 @@ struct DensePolicy {
     __device__ static int num_segments(const Params &, const Tile &) { return 1; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int) {
         Segment s;
-        s.a = p.y; s.lda = p.D; s.K = p.D;
-        s.b_hi = p.w_hi + (size_t)ti.n0 * p.D; s.b_lo = p.w_lo + (size_t)ti.n0 * p.D; s.ldb = p.D; s.b_rows = ti.b_rows;
+        s.a = nullptr; s.lda = 0; s.a_map = &p.map_y; s.a_row0 = ti.row0; s.K = p.D;
+        s.b_hi_map = &p.map_w_hi; s.b_lo_map = &p.map_w_lo; s.b_row0 = ti.n0; s.b_col0 = 0; s.b_box_rows = min(128, p.Hout);
         return s;
     }
     __device__ static int gather_row(const Params &p, const Tile &ti, int, int r) {
@@ -239,7 +271,7 @@ struct DensePolicy {
         const bool ok = row < p.num_nodes;
         for (int c0 = 0; c0 < ti.b_rows; c0 += 16) {
             float v[16];
-            tmem_ld_16cols(tmem_acc + c0, v);
+            tmem_ld_acc16(tmem_acc + c0, v);
             if (ok) {
                 float *orow = p.out + (size_t)row * p.Hout + ti.n0 + c0;
 #pragma unroll
@@ -290,9 +322,9 @@ size_t split_edge_weights_bytes(int num_types, int D, int Kw) { return 2 * ws_sl
 size_t gru_pack_bytes(int H, int D) { return 2 * ws_slice((size_t)(H / 32) * 96 * D, 4) + 2 * ws_slice((size_t)(H / 32) * 96 * H, 4); }
 size_t dense_split_bytes(int Hout, int D) { return 2 * ws_slice((size_t)Hout * D, 4); }
 
-bool supported_message(int H, int D) { return H % 4 == 0 && D % 16 == 0 && H >= 8 && D >= 16; }
-bool supported_gru(int H, int D) { return H % 32 == 0 && D % 4 == 0 && D >= 8; }
-bool supported_dense(int D, int Hout) { return D % 4 == 0 && Hout % 16 == 0 && D >= 8; }
+bool supported_message(int H, int D) { return H % 4 == 0 && D % 16 == 0 && H >= 32 && D >= 16; }
+bool supported_gru(int H, int D) { return H % 32 == 0 && D % 4 == 0 && D >= 32; }
+bool supported_dense(int D, int Hout) { return D % 4 == 0 && Hout % 16 == 0 && D >= 32; }
 
 int edge_messages(const float *h, int H, int D, int use_target, int num_types, const int64_t *type_off,
                   const float *const *weights, const int32_t *src32, const int32_t *tgt32, const int32_t *pos, float *msg,
@@ -310,7 +342,10 @@ int edge_messages(const float *h, int H, int D, int use_target, int num_types, c
     PTGNN_LAUNCHED();
 
     MsgPolicy::Params p{};
-    p.h = h; p.w_hi = w_hi; p.w_lo = w_lo; p.src32 = src32; p.tgt32 = tgt32; p.pos = pos; p.msg = msg;
+    int rc = make_map_2d(&p.map_w_hi, w_hi, (uint64_t)num_types * D, Kw, Kw, D < 128 ? D : 128);
+    if (!rc) rc = make_map_2d(&p.map_w_lo, w_lo, (uint64_t)num_types * D, Kw, Kw, D < 128 ? D : 128);
+    if (rc) return rc;
+    p.h = h; p.src32 = src32; p.tgt32 = tgt32; p.pos = pos; p.msg = msg;
     p.H = H; p.D = D; p.Kw = Kw; p.use_target = use_target; p.num_types = num_types; p.n_blocks = (D + 127) / 128;
     int tiles = 0;
     for (int t = 0; t < num_types; ++t) {
@@ -334,7 +369,15 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
     }
     PTGNN_LAUNCHED();
     GruPolicy::Params p{};
-    p.agg = agg; p.h = h; p.p1_hi = p1_hi; p.p1_lo = p1_lo; p.p2_hi = p2_hi; p.p2_lo = p2_lo; p.b_ih = b_ih; p.b_hh = b_hh;
+    const uint64_t prow = (uint64_t)(H / 32) * 96;
+    int rc = make_map_2d(&p.map_agg, agg, num_nodes, D, D, 128);
+    if (!rc) rc = make_map_2d(&p.map_h, h, num_nodes, H, H, 128);
+    if (!rc) rc = make_map_2d(&p.map_p1_hi, p1_hi, prow, D, D, 96);
+    if (!rc) rc = make_map_2d(&p.map_p1_lo, p1_lo, prow, D, D, 96);
+    if (!rc) rc = make_map_2d(&p.map_p2_hi, p2_hi, prow, H, H, 96);
+    if (!rc) rc = make_map_2d(&p.map_p2_lo, p2_lo, prow, H, H, 96);
+    if (rc) return rc;
+    p.h = h; p.b_ih = b_ih; p.b_hh = b_hh;
     p.out = out; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = H / 32;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_jb;
     return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, st);
@@ -352,7 +395,11 @@ int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const
     }
     PTGNN_LAUNCHED();
     DensePolicy::Params p{};
-    p.y = y; p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.out = out; p.num_nodes = (int)num_nodes; p.D = D; p.Hout = Hout;
+    int rc = make_map_2d(&p.map_y, y, num_nodes, D, D, 128);
+    if (!rc) rc = make_map_2d(&p.map_w_hi, w_hi, Hout, D, D, Hout < 128 ? Hout : 128);
+    if (!rc) rc = make_map_2d(&p.map_w_lo, w_lo, Hout, D, D, Hout < 128 ? Hout : 128);
+    if (rc) return rc;
+    p.bias = bias; p.out = out; p.num_nodes = (int)num_nodes; p.D = D; p.Hout = Hout;
     p.act = act; p.n_blocks = (Hout + 127) / 128;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_blocks;
     return launch_pipeline<DensePolicy>(p, tiles, PTGNN_KERNEL_DENSE, st);
