@@ -128,28 +128,19 @@ struct MsgPolicy {
         g[0] = MmaGroup{ti.b_rows, 0, 0, seg == 0};
         return 1;
     }
-    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane) {
+    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane, float *stage) {
         const int e = ti.e0 + quarter * 32 + lane;
-        const bool ok = e < ti.e_end;
-        float *dst = p.msg;
-        if (ok) dst = p.msg + (size_t)p.pos[e] * p.D + ti.n0;
+        long long row_off = -1;
+        if (e < ti.e_end) row_off = (long long)p.pos[e] * p.D + ti.n0;
         for (int c0 = 0; c0 < ti.b_rows; c0 += 32) {
             if (ti.b_rows - c0 >= 32) {
                 float v[32];
                 tmem_ld_acc32(tmem_acc + c0, v);
-                if (ok) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4 *>(dst + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
+                warp_store_rows<32>(stage, v, p.msg + c0, row_off, lane);
             } else {  // 16-column tail (D % 32 == 16)
                 float v[16];
                 tmem_ld_acc16(tmem_acc + c0, v);
-                if (ok) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<float4 *>(dst + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
+                warp_store_rows<16>(stage, v, p.msg + c0, row_off, lane);
             }
         }
     }
@@ -198,37 +189,28 @@ struct GruPolicy {
         g[1] = MmaGroup{32, 64, 96, true};  // h_n   = h x W_hn^T
         return 2;
     }
-    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane) {
+    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane, float *stage) {
         const int row = ti.row0 + quarter * 32 + lane;
-        const bool ok = row < p.num_nodes;
         const int H = p.H;
+        const long long row_off = row < p.num_nodes ? (long long)row * H + ti.jb * 32 : -1;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            float r[16], z[16], gin[16], ghn[16];
+            float r[16], z[16], gin[16], ghn[16], hval[16];
+            warp_load_rows<16>(stage, hval, p.h + 16 * half, row_off, lane);   // h[row][j0 .. j0+16), coalesced
             tmem_ld_acc16(tmem_acc + 16 * half, r);
             tmem_ld_acc16(tmem_acc + 32 + 16 * half, z);
             tmem_ld_acc16(tmem_acc + 64 + 16 * half, gin);
             tmem_ld_acc16(tmem_acc + 96 + 16 * half, ghn);
-            if (ok) {
-                const int j0 = ti.jb * 32 + 16 * half;
-                const float *hrow = p.h + (size_t)row * H + j0;
-                float *orow = p.out + (size_t)row * H + j0;
+            const int j0 = ti.jb * 32 + 16 * half;
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 hv = *reinterpret_cast<const float4 *>(hrow + 4 * i4);
-                    const float hval[4] = {hv.x, hv.y, hv.z, hv.w};
-                    float o[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = 4 * i4 + u, j = j0 + i;
-                        const float rr = sigmoid_f(r[i] + (p.b_ih[j] + p.b_hh[j]));
-                        const float zz = sigmoid_f(z[i] + (p.b_ih[H + j] + p.b_hh[H + j]));
-                        const float nn = tanhf(gin[i] + p.b_ih[2 * H + j] + rr * (ghn[i] + p.b_hh[2 * H + j]));
-                        o[u] = (1.0f - zz) * nn + zz * hval[u];
-                    }
-                    *reinterpret_cast<float4 *>(orow + 4 * i4) = make_float4(o[0], o[1], o[2], o[3]);
-                }
+            for (int i = 0; i < 16; ++i) {
+                const int j = j0 + i;
+                const float rr = sigmoid_f(r[i] + (p.b_ih[j] + p.b_hh[j]));
+                const float zz = sigmoid_f(z[i] + (p.b_ih[H + j] + p.b_hh[H + j]));
+                const float nn = tanhf(gin[i] + p.b_ih[2 * H + j] + rr * (ghn[i] + p.b_hh[2 * H + j]));
+                r[i] = (1.0f - zz) * nn + zz * hval[i];
             }
+            warp_store_rows<16>(stage, r, p.out + 16 * half, row_off, lane);
         }
     }
 };
@@ -266,25 +248,18 @@ struct DensePolicy {
         g[0] = MmaGroup{ti.b_rows, 0, 0, true};
         return 1;
     }
-    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane) {
+    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane, float *stage) {
         const int row = ti.row0 + quarter * 32 + lane;
-        const bool ok = row < p.num_nodes;
+        const long long row_off = row < p.num_nodes ? (long long)row * p.Hout + ti.n0 : -1;
         for (int c0 = 0; c0 < ti.b_rows; c0 += 16) {
             float v[16];
             tmem_ld_acc16(tmem_acc + c0, v);
-            if (ok) {
-                float *orow = p.out + (size_t)row * p.Hout + ti.n0 + c0;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float b = p.bias ? p.bias[ti.n0 + c0 + i + u] : 0.0f;
-                        o[u] = apply_act(v[i + u] + b, p.act);
-                    }
-                    *reinterpret_cast<float4 *>(orow + i) = make_float4(o[0], o[1], o[2], o[3]);
-                }
+            for (int i = 0; i < 16; ++i) {
+                const float b = p.bias ? p.bias[ti.n0 + c0 + i] : 0.0f;
+                v[i] = apply_act(v[i] + b, p.act);
             }
+            warp_store_rows<16>(stage, v, p.out + c0, row_off, lane);
         }
     }
 };

@@ -26,18 +26,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
+// try_wait without a suspend-time hint = hardware-managed sleep that is woken by the phase flip (a hinted try_wait
+// compiles to NANOSLEEP and was measured to oversleep by ~1 us per wait, which serialised the whole pipeline).
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 21); ++spin) {  // ~1 us suspend hint per try => bounded at a few seconds
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
+        if ((spin & 0xFF) == 0xFF) {          // every 256 failed tries look at the wall clock: give up after 2 s
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
-    __trap();
 }
 
 // ---- proxy / tcgen05 fences ---------------------------------------------------------------------------

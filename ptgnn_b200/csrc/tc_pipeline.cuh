@@ -23,7 +23,9 @@
 //   __device__ static Segment segment(const Params&, const Tile&, int seg);
 //   __device__ static int  gather_row(const Params&, const Tile&, int seg, int r);   only when segment.a_map == nullptr
 //   __device__ static int  mma_groups(const Params&, const Tile&, int seg, MmaGroup (&g)[2]);
-//   __device__ static void epilogue(const Params&, const Tile&, uint32_t tmem_acc, int quarter, int lane);
+//   __device__ static void epilogue(const Params&, const Tile&, uint32_t tmem_acc, int quarter, int lane, float* stage);
+//                          (stage = this warp's 4 KB transpose buffer: TMEM hands every thread one ROW, global memory
+//                           wants warps to touch one row at a time -- see warp_store_rows / warp_load_rows)
 #pragma once
 #include <cuda.h>
 
@@ -42,7 +44,8 @@ constexpr int NUM_THREADS = 9 * 32;
 constexpr int OPERAND_BYTES = TILE_M * CHUNK_K * 4;   // 16 KB: one 128 x 32 fp32 operand tile
 constexpr int SLOT_BYTES = 4 * OPERAND_BYTES;         // A_hi | A_lo | B_hi | B_lo
 constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr int STAGE_BYTES_PER_WARP = 32 * 32 * 4;           // epilogue transpose buffer: 32 rows x 32 fp32
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + 4 * STAGE_BYTES_PER_WARP;
 constexpr int ACC_SET_COLS = 256;                     // 128 main + 128 correction
 constexpr int CORR_OFF = 128;
 
@@ -81,6 +84,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     uint64_t *full = bars, *empty = bars + NUM_SLOTS, *landed = bars + 2 * NUM_SLOTS;
     uint64_t *tmem_full = bars + 3 * NUM_SLOTS, *tmem_empty = bars + 3 * NUM_SLOTS + 2;
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 3 * NUM_SLOTS + 4);
+    float *stage_base = reinterpret_cast<float *>(ring + RING_BYTES + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
             mbar_wait(&tmem_full[acc], acc_use & 1);
             tc_fence_after_sync();
-            Policy::epilogue(p, t, tmem_base + acc * ACC_SET_COLS + ((uint32_t)(quarter * 32) << 16), quarter, lane);
+            Policy::epilogue(p, t, tmem_base + acc * ACC_SET_COLS + ((uint32_t)(quarter * 32) << 16), quarter, lane,
+                             stage_base + quarter * (STAGE_BYTES_PER_WARP / 4));
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -266,6 +271,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     __syncthreads();
     tc_fence_after_sync();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- epilogue transposes through shared memory ---------------------------------------------------------------
+// The accumulator comes out of TMEM one ROW per thread; storing that directly makes every warp-wide store touch 32
+// different 128-byte lines.  Staging 32 rows x NCOLS through a (chunk-XOR-swizzled) buffer lets each store
+// instruction write whole rows: 4 (NCOLS = 32) or 8 (NCOLS = 16) lines per instruction instead of 32.
+// `row_off` is this lane's destination element offset from `dst_base` (negative = row not stored).
+template <int NCOLS>
+__device__ __forceinline__ void warp_store_rows(float *stage, const float (&v)[NCOLS], float *dst_base, long long row_off,
+                                                int lane) {
+    constexpr int CPR = NCOLS / 4;   // 16-byte chunks per row
+#pragma unroll
+    for (int j = 0; j < CPR; ++j)
+        *reinterpret_cast<float4 *>(stage + (lane * CPR + (j ^ (lane & (CPR - 1)))) * 4) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+        const int idx = it * 32 + lane, row = idx / CPR, ch = idx % CPR;
+        const float4 val = *reinterpret_cast<const float4 *>(stage + (row * CPR + (ch ^ (row & (CPR - 1)))) * 4);
+        const long long off = __shfl_sync(0xffffffffu, row_off, row);
+        if (off >= 0) *reinterpret_cast<float4 *>(dst_base + off + ch * 4) = val;
+    }
+    __syncwarp();
+}
+// The mirror image for reads: every lane ends up with NCOLS consecutive floats of ITS row.
+template <int NCOLS>
+__device__ __forceinline__ void warp_load_rows(float *stage, float (&v)[NCOLS], const float *src_base, long long row_off,
+                                               int lane) {
+    constexpr int CPR = NCOLS / 4;
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+        const int idx = it * 32 + lane, row = idx / CPR, ch = idx % CPR;
+        const long long off = __shfl_sync(0xffffffffu, row_off, row);
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off >= 0) val = *reinterpret_cast<const float4 *>(src_base + off + ch * 4);
+        *reinterpret_cast<float4 *>(stage + (row * CPR + (ch ^ (row & (CPR - 1)))) * 4) = val;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) {
+        const float4 val = *reinterpret_cast<const float4 *>(stage + (lane * CPR + (j ^ (lane & (CPR - 1)))) * 4);
+        v[4 * j] = val.x; v[4 * j + 1] = val.y; v[4 * j + 2] = val.z; v[4 * j + 3] = val.w;
+    }
+    __syncwarp();
 }
 
 // accumulator value = main + correction (two TMEM loads)
