@@ -78,7 +78,8 @@ int ptgnn_b200_kernel_timing_read(double *ms /*[host]*/, int64_t *launches /*[ho
  *   status[1]        number of out-of-range indices seen (they are clamped to 0); 0 = valid
  * ---------------------------------------------------------------------------------------------- */
 size_t ptgnn_b200_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges);
-int ptgnn_b200_plan_build(int64_t num_nodes, int32_t num_types,
+int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes /* bound for src ids; <= 0: num_nodes */,
+                          int32_t num_types,
                           const int64_t *const *src_ptrs /*[host] T device pointers*/,
                           const int64_t *const *tgt_ptrs /*[host] T device pointers*/,
                           const int64_t *counts /*[host] T edge counts*/, int32_t *row_ptr, int32_t *perm,
@@ -110,13 +111,17 @@ int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, int64_t num_e
  * edge_weights: [host] array of T device pointers, each nn.Linear.weight [D, H] row-major.
  * gru_*: nn.GRUCell parameters weight_ih [3H, D], weight_hh [3H, H], bias_ih/bias_hh [3H] (gate order r,z,n).
  * type_off: [host] T+1 prefix offsets of the per-type edge counts (edge-id space).
+ * gather_states: rows that the plan's source ids index.  NULL = node_states (the normal, single-GPU case).  For a
+ * node-range shard (multi-GPU split of one connected graph) node_states holds the num_nodes OWNED rows (targets,
+ * local ids) and gather_states the all-gathered [num_source_nodes, H] states (sources, global ids).
  * workspace >= ptgnn_b200_gated_workspace_bytes(...): message buffer [E, D] + aggregate [N, D] + packed / TF32-split
  * weights.  Dimensions that fit the tensor-core tiles (H % 32 == 0, D % 16 == 0) run on tcgen05 (3xTF32, fp32-exact);
  * other multiples of 4 run on the FFMA kernels.  PTGNN_B200_DISABLE_TC=1 forces the FFMA kernels.
  * ---------------------------------------------------------------------------------------------- */
 size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t state_dim,
                                         int32_t message_dim);
-int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, int32_t state_dim, int32_t message_dim,
+int ptgnn_b200_gated_forward_f32(const float *node_states, const float *gather_states /* NULL: node_states */,
+                                 int64_t num_nodes, int32_t state_dim, int32_t message_dim,
                                  int32_t num_types, const int64_t *type_off /*[host]*/, const int32_t *row_ptr,
                                  const int32_t *pos, const int32_t *src32,
                                  const float *const *edge_weights /*[host] T device pointers*/, const float *gru_w_ih,
@@ -132,7 +137,8 @@ int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, in
  * ---------------------------------------------------------------------------------------------- */
 size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t in_dim,
                                       int32_t message_dim, int32_t out_dim, int32_t use_target_state);
-int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_nodes, int32_t in_dim, int32_t message_dim,
+int ptgnn_b200_mlp_forward_f32(const float *node_states, const float *gather_states /* NULL: node_states */,
+                               int64_t num_nodes, int32_t in_dim, int32_t message_dim,
                                int32_t out_dim, int32_t num_types, const int64_t *type_off /*[host]*/,
                                const int32_t *row_ptr, const int32_t *pos, const int32_t *src32, const int32_t *tgt32,
                                const float *const *edge_weights /*[host] T device pointers*/,

@@ -25,15 +25,15 @@ SIGNATURES = {
     "ptgnn_b200_kernel_timing_enable": (ctypes.c_int, [c_i32]),
     "ptgnn_b200_kernel_timing_read": (ctypes.c_int, [c_void_p, c_void_p, c_i32]),
     "ptgnn_b200_plan_workspace_bytes": (c_size_t, [c_i64, c_i64]),
-    "ptgnn_b200_plan_build": (ctypes.c_int, [c_i64, c_i32, c_void_p, c_void_p, c_void_p] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "ptgnn_b200_plan_build": (ctypes.c_int, [c_i64, c_i64, c_i32, c_void_p, c_void_p, c_void_p] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_segment_reduce_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
     "ptgnn_b200_scatter_workspace_bytes": (c_size_t, [c_i64, c_i64]),
     "ptgnn_b200_scatter_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_gated_workspace_bytes": (c_size_t, [c_i64, c_i64, c_i32, c_i32, c_i32]),
-    "ptgnn_b200_gated_forward_f32": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "ptgnn_b200_gated_forward_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                     c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_mlp_workspace_bytes": (c_size_t, [c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32]),
-    "ptgnn_b200_mlp_forward_f32": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "ptgnn_b200_mlp_forward_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_f32, c_void_p, c_void_p, c_i32,
                                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_gated_gnn_forward_host_f32": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32,

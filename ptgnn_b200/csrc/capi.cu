@@ -125,7 +125,7 @@ extern "C" int ptgnn_b200_gated_gnn_forward_host_f32(const float *node_states, i
     const size_t ws_layer = ptgnn_b200_gated_workspace_bytes(num_nodes, E, num_types, H, H);
     const size_t ws_bytes = ws_plan > ws_layer ? ws_plan : ws_layer;
     PTGNN_CUDA(d_ws.alloc(ws_bytes));
-    int rc = ptgnn_b200_plan_build(num_nodes, num_types, dsrc.data(), dtgt.data(), counts, row_ptr, perm, pos, src_sorted,
+    int rc = ptgnn_b200_plan_build(num_nodes, num_nodes, num_types, dsrc.data(), dtgt.data(), counts, row_ptr, perm, pos, src_sorted,
                                    d_etype.as<uint8_t>(), src32, tgt32, d_status.as<int32_t>(), d_ws.p, ws_bytes, st);
     if (rc) return rc;
 
@@ -151,7 +151,7 @@ extern "C" int ptgnn_b200_gated_gnn_forward_host_f32(const float *node_states, i
         for (int t = 0; t < num_types; ++t) dev_w[t] = base + (size_t)t * H * H;
         float *wih = base + (size_t)num_types * H * H, *whh = wih + 3 * (size_t)H * H;
         float *bih = whh + 3 * (size_t)H * H, *bhh = bih + 3 * H;
-        rc = ptgnn_b200_gated_forward_f32(d_state[cur].as<float>(), num_nodes, H, H, num_types, type_off.data(), row_ptr,
+        rc = ptgnn_b200_gated_forward_f32(d_state[cur].as<float>(), nullptr, num_nodes, H, H, num_types, type_off.data(), row_ptr,
                                           pos, src32, dev_w.data(), wih, whh, bih, bhh, reduce,
                                           d_state[cur ^ 1].as<float>(), d_ws.p, ws_bytes, st);
         if (rc) return rc;

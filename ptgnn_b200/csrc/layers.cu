@@ -30,7 +30,8 @@ struct MsgParams {
 
 template <int TN>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-edge_message_kernel(const __grid_constant__ MsgParams p, const float *__restrict__ h, int H, int use_target, int D,
+edge_message_kernel(const __grid_constant__ MsgParams p, const float *__restrict__ h, const float *__restrict__ h_tgt,
+                    int H, int use_target, int D,
                     const int32_t *__restrict__ src32, const int32_t *__restrict__ tgt32,
                     const int32_t *__restrict__ pos, float *__restrict__ msg) {
     using Tile = GemmTile<TN>;
@@ -68,7 +69,7 @@ edge_message_kernel(const __grid_constant__ MsgParams p, const float *__restrict
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
 
     AOperand A;
-    A.a0 = h; A.a1 = h; A.ld0 = H; A.ld1 = H; A.K0 = H; A.K = use_target ? 2 * H : H;
+    A.a0 = h; A.a1 = h_tgt; A.ld0 = H; A.ld1 = H; A.K0 = H; A.K = use_target ? 2 * H : H;
     const int n0 = blockIdx.y * Tile::BN;
     gemm_mainloop<TN, 0>(acc, pipe, A, s_idx0, s_idx1, p.weights[t], A.K, n0, D);
 
@@ -221,7 +222,7 @@ static int set_smem(K kernel, int bytes) {
     return PTGNN_OK;
 }
 
-static int launch_edge_messages(const float *h, int H, int D, int use_target, int num_types, const int64_t *type_off,
+static int launch_edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_target, int num_types, const int64_t *type_off,
                                 const float *const *weights, const int32_t *src32, const int32_t *tgt32,
                                 const int32_t *pos, float *msg, cudaStream_t st) {
     MsgParams p{};
@@ -245,7 +246,7 @@ static int launch_edge_messages(const float *h, int H, int D, int use_target, in
         dim3 grid(tiles, (unsigned)ceil_div(D, Tile::BN));
         {
             TimedScope timed__(PTGNN_KERNEL_MESSAGE, st);
-            edge_message_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h, H, use_target, D, src32, tgt32, pos, msg);
+            edge_message_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h_src, h_tgt, H, use_target, D, src32, tgt32, pos, msg);
         }
     } else {
         using Tile = GemmTile<8>;
@@ -254,7 +255,7 @@ static int launch_edge_messages(const float *h, int H, int D, int use_target, in
         dim3 grid(tiles, (unsigned)ceil_div(D, Tile::BN));
         {
             TimedScope timed__(PTGNN_KERNEL_MESSAGE, st);
-            edge_message_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h, H, use_target, D, src32, tgt32, pos, msg);
+            edge_message_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(p, h_src, h_tgt, H, use_target, D, src32, tgt32, pos, msg);
         }
     }
     PTGNN_LAUNCHED();
@@ -316,7 +317,8 @@ extern "C" size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t nu
     return gated_ws_layout(num_nodes, num_edges, num_types, state_dim, message_dim).total;
 }
 
-extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t num_nodes, int32_t state_dim,
+extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
+                                            int32_t state_dim,
                                             int32_t message_dim, int32_t num_types, const int64_t *type_off,
                                             const int32_t *row_ptr, const int32_t *pos, const int32_t *src32,
                                             const float *const *edge_weights, const float *gru_w_ih,
@@ -347,13 +349,15 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, int64_t nu
     char *ws = static_cast<char *>(workspace);
     float *msg = reinterpret_cast<float *>(ws + L.msg), *agg = reinterpret_cast<float *>(ws + L.agg);
     float *P1 = reinterpret_cast<float *>(ws + L.p1), *P2 = reinterpret_cast<float *>(ws + L.p2);
+    const float *gsrc = gather_states ? gather_states : node_states;   // rows that `src32` indexes (sharded runs)
 
     // 1. per-edge messages, written at their target-sorted positions
     if (tc_enabled() && tc::supported_message(H, D)) {
-        rc = tc::edge_messages(node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg,
+        rc = tc::edge_messages(gsrc, node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg,
                                ws + L.wsplit, st);
     } else {
-        rc = launch_edge_messages(node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg, st);
+        rc = launch_edge_messages(gsrc, node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg,
+                                  st);
     }
     if (rc) return rc;
     // 2. streaming segmented reduce
@@ -388,7 +392,8 @@ extern "C" size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_
     return mlp_ws_layout(num_nodes, num_edges, num_types, in_dim, message_dim, out_dim, use_target_state).total;
 }
 
-extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_nodes, int32_t in_dim,
+extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
+                                          int32_t in_dim,
                                           int32_t message_dim, int32_t out_dim, int32_t num_types,
                                           const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
                                           const int32_t *src32, const int32_t *tgt32, const float *const *edge_weights,
@@ -422,12 +427,14 @@ extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, int64_t num_
     float *msg = reinterpret_cast<float *>(ws + L.msg);
     float *y = dense_weight ? reinterpret_cast<float *>(ws + L.y) : out_states;
     const int ut = use_target_state ? 1 : 0;
+    const float *gsrc = gather_states ? gather_states : node_states;   // rows that `src32` indexes (sharded runs)
 
     if (tc_enabled() && tc::supported_message(H, D)) {
-        rc = tc::edge_messages(node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg,
+        rc = tc::edge_messages(gsrc, node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg,
                                ws + L.wsplit, st);
     } else {
-        rc = launch_edge_messages(node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg, st);
+        rc = launch_edge_messages(gsrc, node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg,
+                                  st);
     }
     if (rc) return rc;
     ReduceEpilogue epi{message_activation, ln_weight, ln_bias, ln_eps};

@@ -88,7 +88,7 @@ __global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const floa
 struct MsgPolicy {
     struct Params {
         CUtensorMap map_w_hi, map_w_lo;   // [T*D, Kw], box {32, min(128, D)}
-        const float *h;
+        const float *h, *h_tgt;           // rows indexed by src32 / by tgt32
         const int32_t *src32, *tgt32, *pos;
         float *msg;
         int H, D, Kw, use_target, num_types, n_blocks;
@@ -114,7 +114,7 @@ struct MsgPolicy {
     __device__ static int num_segments(const Params &p, const Tile &) { return p.use_target ? 2 : 1; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
         Segment s;
-        s.a = p.h; s.lda = p.H; s.K = p.H; s.a_map = nullptr; s.a_row0 = 0;
+        s.a = seg == 0 ? p.h : p.h_tgt; s.lda = p.H; s.K = p.H; s.a_map = nullptr; s.a_row0 = 0;
         s.b_hi_map = &p.map_w_hi; s.b_lo_map = &p.map_w_lo;
         s.b_row0 = ti.t * p.D + ti.n0; s.b_col0 = seg * p.H; s.b_box_rows = min(128, p.D);
         return s;
@@ -301,7 +301,7 @@ bool supported_message(int H, int D) { return H % 4 == 0 && D % 16 == 0 && H >= 
 bool supported_gru(int H, int D) { return H % 32 == 0 && D % 4 == 0 && D >= 32; }
 bool supported_dense(int D, int Hout) { return D % 4 == 0 && Hout % 16 == 0 && D >= 32; }
 
-int edge_messages(const float *h, int H, int D, int use_target, int num_types, const int64_t *type_off,
+int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_target, int num_types, const int64_t *type_off,
                   const float *const *weights, const int32_t *src32, const int32_t *tgt32, const int32_t *pos, float *msg,
                   void *scratch, cudaStream_t st) {
     const int Kw = use_target ? 2 * H : H;
@@ -320,7 +320,7 @@ int edge_messages(const float *h, int H, int D, int use_target, int num_types, c
     int rc = make_map_2d(&p.map_w_hi, w_hi, (uint64_t)num_types * D, Kw, Kw, D < 128 ? D : 128);
     if (!rc) rc = make_map_2d(&p.map_w_lo, w_lo, (uint64_t)num_types * D, Kw, Kw, D < 128 ? D : 128);
     if (rc) return rc;
-    p.h = h; p.src32 = src32; p.tgt32 = tgt32; p.pos = pos; p.msg = msg;
+    p.h = h_src; p.h_tgt = h_tgt; p.src32 = src32; p.tgt32 = tgt32; p.pos = pos; p.msg = msg;
     p.H = H; p.D = D; p.Kw = Kw; p.use_target = use_target; p.num_types = num_types; p.n_blocks = (D + 127) / 128;
     int tiles = 0;
     for (int t = 0; t < num_types; ++t) {

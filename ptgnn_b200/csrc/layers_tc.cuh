@@ -13,8 +13,8 @@ size_t split_edge_weights_bytes(int num_types, int D, int Kw);
 size_t gru_pack_bytes(int H, int D);
 size_t dense_split_bytes(int Hout, int D);
 
-// messages[pos[e]] = W_t(e) [h_src(e) ; h_tgt(e)]          (scratch >= split_edge_weights_bytes)
-int edge_messages(const float *h, int H, int D, int use_target, int num_types, const int64_t *type_off,
+// messages[pos[e]] = W_t(e) [h_src[src(e)] ; h_tgt[tgt(e)]]   (scratch >= split_edge_weights_bytes)
+int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_target, int num_types, const int64_t *type_off,
                   const float *const *weights, const int32_t *src32, const int32_t *tgt32, const int32_t *pos, float *msg,
                   void *scratch, cudaStream_t st);
 // out = GRUCell(agg, h)                                     (scratch >= gru_pack_bytes)

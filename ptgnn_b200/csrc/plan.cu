@@ -125,7 +125,7 @@ static int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int32_
 // pass 0: int64 -> int32 down-conversion, range check, in-degree histogram
 // =================================================================================================
 __global__ void __launch_bounds__(256) convert_count_kernel(const __grid_constant__ EdgeTables tabs, int64_t num_nodes,
-                                                            int64_t num_edges, int32_t *__restrict__ src32,
+                                                            int64_t num_source_nodes, int64_t num_edges, int32_t *__restrict__ src32,
                                                             int32_t *__restrict__ tgt32, int32_t *__restrict__ deg,
                                                             int32_t *__restrict__ status) {
     int bad = 0;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) convert_count_kernel(const __grid_constan
         const int t = type_of_edge(tabs.off, tabs.num_types, e);
         const int64_t i = e - tabs.off[t];
         int64_t s = tabs.src[t][i], v = tabs.tgt[t][i];
-        if (s < 0 || s >= num_nodes) { s = 0; ++bad; }
+        if (s < 0 || s >= num_source_nodes) { s = 0; ++bad; }
         if (v < 0 || v >= num_nodes) { v = 0; ++bad; }
         src32[e] = (int32_t)s;
         tgt32[e] = (int32_t)v;
@@ -308,13 +308,16 @@ extern "C" size_t ptgnn_b200_plan_workspace_bytes(int64_t num_nodes, int64_t num
     return plan_ws_layout(num_nodes, num_edges).total;
 }
 
-extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int32_t num_types, const int64_t *const *src_ptrs,
+extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
+                                     const int64_t *const *src_ptrs,
                                      const int64_t *const *tgt_ptrs, const int64_t *counts, int32_t *row_ptr,
                                      int32_t *perm, int32_t *pos, int32_t *src_sorted, uint8_t *etype_sorted,
                                      int32_t *src32, int32_t *tgt32, int32_t *status, void *workspace,
                                      size_t workspace_bytes, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PTGNN_CHECK_ARG(num_nodes >= 0 && num_nodes < INT32_MAX, "plan_build: num_nodes=%lld out of range", (long long)num_nodes);
+    if (num_source_nodes <= 0) num_source_nodes = num_nodes;
+    PTGNN_CHECK_ARG(num_source_nodes < INT32_MAX, "plan_build: num_source_nodes out of range");
     PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES, "plan_build: num_types=%d (max %d)", num_types,
                     PTGNN_MAX_EDGE_TYPES);
     PTGNN_CHECK_ARG(row_ptr && status, "plan_build: null row_ptr/status");
@@ -356,7 +359,7 @@ extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int32_t num_types, const
     const unsigned grid = (unsigned)(ceil_div(E, 256) < 148 * 16 ? ceil_div(E, 256) : 148 * 16);
     {
         TimedScope timed__(PTGNN_KERNEL_PLAN, st);
-        convert_count_kernel<<<grid, 256, 0, st>>>(tabs, num_nodes, E, src32, tgt32, deg, status);
+        convert_count_kernel<<<grid, 256, 0, st>>>(tabs, num_nodes, num_source_nodes, E, src32, tgt32, deg, status);
     }
     PTGNN_LAUNCHED();
     // row_ptr[0..N] = exclusive scan of deg[0..N] (deg[N] == 0, so row_ptr[N] == E)

@@ -33,11 +33,32 @@ static int launch_shape(const float *msg, const int32_t *row_ptr, const int32_t 
     return PTGNN_OK;
 }
 
+template <int RED, int CHUNKS>
+static int launch_stream(const float *msg, const int32_t *row_ptr, const int32_t *perm, int64_t N, int D, float *out,
+                         const ReduceEpilogue *epi, cudaStream_t st) {
+    const unsigned grid = (unsigned)ceil_div(N, 8 * 16);   // 8 warps x 16 rows per block
+    ReduceEpilogue e{};
+    if (epi) e = *epi;
+    {
+        TimedScope timed__(PTGNN_KERNEL_REDUCE, st);
+        if (epi) segment_reduce_stream_kernel<RED, CHUNKS, true><<<grid, 256, 0, st>>>(msg, row_ptr, perm, (int)N, D, out, e);
+        else segment_reduce_stream_kernel<RED, CHUNKS, false><<<grid, 256, 0, st>>>(msg, row_ptr, perm, (int)N, D, out, e);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
 template <int RED>
 static int launch_red(const float *msg, const int32_t *row_ptr, const int32_t *perm, int64_t N, int64_t E, int D,
                       float *out, int64_t *arg_out, const ReduceEpilogue *epi, cudaStream_t st) {
     if (D <= 32) return launch_shape<RED, 8, 1>(msg, row_ptr, perm, N, E, D, out, arg_out, epi, st);
     if (D <= 64) return launch_shape<RED, 16, 1>(msg, row_ptr, perm, N, E, D, out, arg_out, epi, st);
+    const bool want_arg = arg_out && (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN);
+    if (!want_arg) {   // wide rows without arg: streaming kernel
+        if (D <= 128) return launch_stream<RED, 1>(msg, row_ptr, perm, N, D, out, epi, st);
+        if (D <= 256) return launch_stream<RED, 2>(msg, row_ptr, perm, N, D, out, epi, st);
+        return launch_stream<RED, 4>(msg, row_ptr, perm, N, D, out, epi, st);
+    }
     if (D <= 128) return launch_shape<RED, 32, 1>(msg, row_ptr, perm, N, E, D, out, arg_out, epi, st);
     if (D <= 256) return launch_shape<RED, 32, 2>(msg, row_ptr, perm, N, E, D, out, arg_out, epi, st);
     return launch_shape<RED, 32, 4>(msg, row_ptr, perm, N, E, D, out, arg_out, epi, st);
@@ -111,7 +132,7 @@ extern "C" int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, in
     // torch_scatter treats `index` as both the (unused) source and the target list: a 1-type edge set.
     const int64_t *ptrs[1] = {index};
     const int64_t counts[1] = {num_edges};
-    int rc = ptgnn_b200_plan_build(num_nodes, 1, ptrs, ptrs, counts, p32(L.row_ptr), p32(L.perm), p32(L.pos),
+    int rc = ptgnn_b200_plan_build(num_nodes, num_nodes, 1, ptrs, ptrs, counts, p32(L.row_ptr), p32(L.perm), p32(L.pos),
                                    p32(L.src_sorted), reinterpret_cast<uint8_t *>(ws + L.etype_sorted), p32(L.src32),
                                    p32(L.tgt32), p32(L.status), ws + L.plan, workspace_bytes - L.plan, stream);
     if (rc) return rc;

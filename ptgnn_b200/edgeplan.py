@@ -21,11 +21,14 @@ class EdgePlan:
     """Device-resident CSR-by-target plan (all int32 unless noted).  Field meanings: include/ptgnn_b200.h."""
 
     __slots__ = (
-        "num_nodes", "num_edges", "num_types", "type_off", "type_off_c", "row_ptr", "perm", "pos", "src_sorted",
+        "num_nodes", "num_source_nodes", "num_edges", "num_types", "type_off", "type_off_c", "row_ptr", "perm", "pos", "src_sorted",
         "etype_sorted", "src32", "tgt32", "status", "device", "_keepalive", "_validated",
     )
 
-    def __init__(self, adjacency_lists: Adjacency, num_nodes: int, validate: bool = False):
+    def __init__(self, adjacency_lists: Adjacency, num_nodes: int, validate: bool = False,
+                 num_source_nodes: Optional[int] = None):
+        """``num_nodes`` = number of TARGET rows (CSR rows).  ``num_source_nodes`` (default: the same) bounds the source
+        ids; it differs only for node-range shards, where targets are local rows and sources index the gathered states."""
         if len(adjacency_lists) > 128:
             raise NotImplementedError("more than 128 edge types")
         if len(adjacency_lists) == 0:
@@ -39,6 +42,7 @@ class EdgePlan:
                 raise ValueError("adjacency lists must be pairs of equal-length 1-D tensors")
         E = sum(counts)
         self.num_nodes, self.num_edges, self.num_types, self.device = int(num_nodes), E, len(counts), device
+        self.num_source_nodes = int(num_source_nodes) if num_source_nodes is not None else int(num_nodes)
         self.type_off = [0]
         for c in counts:
             self.type_off.append(self.type_off[-1] + c)
@@ -56,7 +60,7 @@ class EdgePlan:
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):
             rc = lib.ptgnn_b200_plan_build(
-                num_nodes, len(counts), N.ptr_table(srcs), N.ptr_table(tgts), N.i64_array(counts),
+                num_nodes, self.num_source_nodes, len(counts), N.ptr_table(srcs), N.ptr_table(tgts), N.i64_array(counts),
                 N.ptr(self.row_ptr), N.ptr(self.perm), N.ptr(self.pos), N.ptr(self.src_sorted), N.ptr(self.etype_sorted),
                 N.ptr(self.src32), N.ptr(self.tgt32), N.ptr(self.status), N.ptr(ws), ws_bytes, N.current_stream(device),
             )
@@ -71,7 +75,7 @@ class EdgePlan:
         if not self._validated:
             bad = int(self.status.item())
             if bad:
-                raise IndexError(f"{bad} edge indices outside [0, {self.num_nodes})")
+                raise IndexError(f"{bad} edge indices outside [0, {self.num_nodes}) (targets) / [0, {self.num_source_nodes}) (sources)")
             self._validated = True
 
 
@@ -80,24 +84,25 @@ _CACHE: "OrderedDict[tuple, EdgePlan]" = OrderedDict()
 _CACHE_SIZE = 4
 
 
-def _key(adjacency_lists: Adjacency, num_nodes: int) -> tuple:
-    parts: List[int] = [num_nodes]
+def _key(adjacency_lists: Adjacency, num_nodes: int, num_source_nodes: Optional[int] = None) -> tuple:
+    parts: List[int] = [num_nodes, -1 if num_source_nodes is None else num_source_nodes]
     for s, t in adjacency_lists:
         parts += [s.data_ptr(), s.shape[0], s._version, t.data_ptr(), t._version]
     return tuple(parts)
 
 
-def plan_for(adjacency_lists: Adjacency, num_nodes: int, plan: Optional[EdgePlan] = None) -> EdgePlan:
+def plan_for(adjacency_lists: Adjacency, num_nodes: int, plan: Optional[EdgePlan] = None,
+             num_source_nodes: Optional[int] = None) -> EdgePlan:
     """Returns the plan for these adjacency tensors, building it on a cache miss.  Entries keep their index tensors
     alive, so a (data_ptr, version) key cannot alias different contents."""
     if plan is not None:
         return plan
-    key = _key(adjacency_lists, num_nodes)
+    key = _key(adjacency_lists, num_nodes, num_source_nodes)
     hit = _CACHE.get(key)
     if hit is not None:
         _CACHE.move_to_end(key)
         return hit
-    built = EdgePlan(adjacency_lists, num_nodes)
+    built = EdgePlan(adjacency_lists, num_nodes, num_source_nodes=num_source_nodes)
     _CACHE[key] = built
     while len(_CACHE) > _CACHE_SIZE:
         _CACHE.popitem(last=False)

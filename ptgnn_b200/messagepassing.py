@@ -80,8 +80,19 @@ class AbstractMessagePassingLayer(nn.Module):
             messages.dtype
         )
 
-    def _plan(self, adjacency_lists, num_nodes: int) -> EdgePlan:
-        return plan_for(adjacency_lists, num_nodes, AbstractMessagePassingLayer._shared_plan)
+    def _plan(self, adjacency_lists, num_nodes: int, num_source_nodes: Optional[int] = None) -> EdgePlan:
+        return plan_for(adjacency_lists, num_nodes, AbstractMessagePassingLayer._shared_plan, num_source_nodes)
+
+    @staticmethod
+    def _gather_source(gather_states: Optional[torch.Tensor], h: torch.Tensor) -> Optional[torch.Tensor]:
+        """Node-range shards (ptgnn_b200.sharding): `node_states` holds this rank's rows (targets, local ids) and
+        `gather_states` the all-gathered states that the source ids index.  None in the ordinary single-GPU case."""
+        if gather_states is None:
+            return None
+        g = N.require_cuda(gather_states, "gather_states", torch.float32)
+        if g.dim() != 2 or g.shape[1] != h.shape[1]:
+            raise ValueError("gather_states must be [num_source_nodes, H]")
+        return g
 
     @property
     @abstractmethod
@@ -145,6 +156,7 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         reference_node_ids: Dict[str, torch.Tensor] = None,
         reference_node_graph_idx: Dict[str, torch.Tensor] = None,
         edge_features: List[torch.Tensor] = None,
+        gather_states: Optional[torch.Tensor] = None,
     ) -> torch.Tensor:
         linears = self.__edge_message_transformation_layers
         assert len(adjacency_lists) == len(linears), "one adjacency list per edge type is required"
@@ -159,7 +171,8 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         h = N.require_cuda(node_states, "node_states", torch.float32)
         num_nodes, H = h.shape
         D = self.__message_dimension
-        plan = self._plan(adjacency_lists, num_nodes)
+        gsrc = self._gather_source(gather_states, h)
+        plan = self._plan(adjacency_lists, num_nodes, None if gsrc is None else gsrc.shape[0])
         gru = self.__state_update
         weights = [N.require_cuda(lin.weight, "edge weight", torch.float32) for lin in linears]
         w_ih, w_hh = N.require_cuda(gru.weight_ih, "weight_ih", torch.float32), N.require_cuda(gru.weight_hh, "weight_hh", torch.float32)
@@ -171,7 +184,7 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         out = torch.empty_like(h)
         with torch.cuda.device(h.device):
             rc = lib.ptgnn_b200_gated_forward_f32(
-                N.ptr(h), num_nodes, H, D, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
+                N.ptr(h), N.ptr(gsrc), num_nodes, H, D, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
                 N.ptr(plan.src32), N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce,
                 N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
             )
@@ -288,6 +301,7 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         reference_node_ids: Dict[str, torch.Tensor] = None,
         reference_node_graph_idx: Dict[str, torch.Tensor] = None,
         edge_features: List[torch.Tensor] = None,
+        gather_states: Optional[torch.Tensor] = None,
     ) -> torch.Tensor:
         mlps = self.__edge_message_transformation_layers
         assert len(adjacency_lists) == len(mlps), "The number of adjacency lists must be equal to the number of edge types."
@@ -320,7 +334,8 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         num_nodes, H = h.shape
         D = self.__message_dim
         out_dim = dense.out_features if dense is not None else D
-        plan = self._plan(adjacency_lists, num_nodes)
+        gsrc = self._gather_source(gather_states, h)
+        plan = self._plan(adjacency_lists, num_nodes, None if gsrc is None else gsrc.shape[0])
         weights = [N.require_cuda(m.single_linear.weight, "edge weight", torch.float32) for m in mlps]
         f32 = lambda t, n: None if t is None else N.require_cuda(t, n, torch.float32)  # noqa: E731
         ln_w, ln_b = (f32(ln.weight, "ln.weight"), f32(ln.bias, "ln.bias")) if ln is not None else (None, None)
@@ -334,7 +349,7 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         out = torch.empty(num_nodes, out_dim, dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):
             rc = lib.ptgnn_b200_mlp_forward_f32(
-                N.ptr(h), num_nodes, H, D, out_dim, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
+                N.ptr(h), N.ptr(gsrc), num_nodes, H, D, out_dim, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
                 N.ptr(plan.src32), N.ptr(plan.tgt32), N.ptr_table(weights), int(self.__use_target_state_as_message_input),
                 reduce, msg_act, N.ptr(ln_w), N.ptr(ln_b), float(ln.eps) if ln is not None else 0.0, N.ptr(d_w), N.ptr(d_b),
                 dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
