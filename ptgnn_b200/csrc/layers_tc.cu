@@ -3,6 +3,8 @@
 // tc_pipeline.cuh, the policies below only say where rows come from and what the epilogue does with the tile.
 #include "layers_tc.cuh"
 
+#include <stdlib.h>
+
 #include "tc_pipeline.cuh"
 
 namespace ptgnn {
@@ -91,7 +93,7 @@ struct MsgPolicy {
         const float *h, *h_tgt;           // rows indexed by src32 / by tgt32
         const int32_t *src32, *tgt32, *pos;
         float *msg;
-        int H, D, Kw, use_target, num_types, n_blocks;
+        int H, D, Kw, use_target, num_types, n_blocks, dbg;
         int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
         int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
     };
@@ -128,20 +130,21 @@ struct MsgPolicy {
         g[0] = MmaGroup{ti.b_rows, 0, 0, seg == 0};
         return 1;
     }
-    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane, float *stage) {
+    // warp `half` owns accumulator columns [64*half, 64*half + 64)
+    __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
+        const int c0 = 64 * half;
+        if (c0 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0, &acc[0]);
+        if (c0 + 32 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0 + 32, &acc[32]);
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], int quarter, int half, int lane, float *stage) {
         const int e = ti.e0 + quarter * 32 + lane;
         long long row_off = -1;
         if (e < ti.e_end) row_off = (long long)p.pos[e] * p.D + ti.n0;
-        for (int c0 = 0; c0 < ti.b_rows; c0 += 32) {
-            if (ti.b_rows - c0 >= 32) {
-                float v[32];
-                tmem_ld_acc32(tmem_acc + c0, v);
-                warp_store_rows<32>(stage, v, p.msg + c0, row_off, lane);
-            } else {  // 16-column tail (D % 32 == 16)
-                float v[16];
-                tmem_ld_acc16(tmem_acc + c0, v);
-                warp_store_rows<16>(stage, v, p.msg + c0, row_off, lane);
-            }
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+            const int c0 = 64 * half + 32 * cb;
+            if (ti.b_rows - c0 >= 32) warp_store_rows<32>(stage, &acc[32 * cb], p.msg + c0, row_off, lane);
+            else if (ti.b_rows - c0 >= 16) warp_store_rows<16>(stage, &acc[32 * cb], p.msg + c0, row_off, lane);   // D % 32 == 16
         }
     }
 };
@@ -156,7 +159,7 @@ struct GruPolicy {
         const float *h;
         const float *b_ih, *b_hh;
         float *out;
-        int num_nodes, H, D, n_jb;
+        int num_nodes, H, D, n_jb, dbg;
     };
     struct Tile { int row0, jb; };
 
@@ -189,29 +192,28 @@ struct GruPolicy {
         g[1] = MmaGroup{32, 64, 96, true};  // h_n   = h x W_hn^T
         return 2;
     }
-    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane, float *stage) {
+    // accumulator columns: [0,32) r | [32,64) z | [64,96) i_n | [96,128) h_n (pre-activations without biases);
+    // warp `half` owns hidden units j0 + 16*half .. +16 and therefore 16 columns of each gate group
+    __device__ static void drain(const Params &, const Tile &, uint32_t tmem_lane, int half, float (&acc)[64]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld_sum16(tmem_lane + 32 * g + 16 * half, &acc[16 * g]);
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], int quarter, int half, int lane, float *stage) {
         const int row = ti.row0 + quarter * 32 + lane;
         const int H = p.H;
-        const long long row_off = row < p.num_nodes ? (long long)row * H + ti.jb * 32 : -1;
+        const int j0 = ti.jb * 32 + 16 * half;
+        const long long row_off = row < p.num_nodes ? (long long)row * H + j0 : -1;
+        float hval[16];
+        warp_load_rows<16>(stage, hval, p.h, row_off, lane);   // h[row][j0 .. j0+16), coalesced
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float r[16], z[16], gin[16], ghn[16], hval[16];
-            warp_load_rows<16>(stage, hval, p.h + 16 * half, row_off, lane);   // h[row][j0 .. j0+16), coalesced
-            tmem_ld_acc16(tmem_acc + 16 * half, r);
-            tmem_ld_acc16(tmem_acc + 32 + 16 * half, z);
-            tmem_ld_acc16(tmem_acc + 64 + 16 * half, gin);
-            tmem_ld_acc16(tmem_acc + 96 + 16 * half, ghn);
-            const int j0 = ti.jb * 32 + 16 * half;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int j = j0 + i;
-                const float rr = sigmoid_f(r[i] + (p.b_ih[j] + p.b_hh[j]));
-                const float zz = sigmoid_f(z[i] + (p.b_ih[H + j] + p.b_hh[H + j]));
-                const float nn = tanhf(gin[i] + p.b_ih[2 * H + j] + rr * (ghn[i] + p.b_hh[2 * H + j]));
-                r[i] = (1.0f - zz) * nn + zz * hval[i];
-            }
-            warp_store_rows<16>(stage, r, p.out + 16 * half, row_off, lane);
+        for (int i = 0; i < 16; ++i) {
+            const int j = j0 + i;
+            const float rr = sigmoid_f(acc[i] + (p.b_ih[j] + p.b_hh[j]));
+            const float zz = sigmoid_f(acc[16 + i] + (p.b_ih[H + j] + p.b_hh[H + j]));
+            const float nn = tanhf(acc[32 + i] + p.b_ih[2 * H + j] + rr * (acc[48 + i] + p.b_hh[2 * H + j]));
+            hval[i] = (1.0f - zz) * nn + zz * hval[i];
         }
+        warp_store_rows<16>(stage, hval, p.out, row_off, lane);
     }
 };
 
@@ -223,7 +225,7 @@ struct DensePolicy {
         CUtensorMap map_y, map_w_hi, map_w_lo;   // [N, D] box {32,128}; [Hout, D] box {32, min(128, Hout)}
         const float *bias;
         float *out;
-        int num_nodes, D, Hout, act, n_blocks;
+        int num_nodes, D, Hout, act, n_blocks, dbg;
     };
     struct Tile { int row0, n0, b_rows; };
 
@@ -248,18 +250,25 @@ struct DensePolicy {
         g[0] = MmaGroup{ti.b_rows, 0, 0, true};
         return 1;
     }
-    __device__ static void epilogue(const Params &p, const Tile &ti, uint32_t tmem_acc, int quarter, int lane, float *stage) {
+    __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
+        const int c0 = 64 * half;
+        if (c0 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0, &acc[0]);
+        if (c0 + 32 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0 + 32, &acc[32]);
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], int quarter, int half, int lane, float *stage) {
         const int row = ti.row0 + quarter * 32 + lane;
         const long long row_off = row < p.num_nodes ? (long long)row * p.Hout + ti.n0 : -1;
-        for (int c0 = 0; c0 < ti.b_rows; c0 += 16) {
-            float v[16];
-            tmem_ld_acc16(tmem_acc + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float b = p.bias ? p.bias[ti.n0 + c0 + i] : 0.0f;
-                v[i] = apply_act(v[i] + b, p.act);
+        for (int cb = 0; cb < 4; ++cb) {
+            const int c0 = 64 * half + 16 * cb;
+            if (c0 < ti.b_rows) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float b = p.bias ? p.bias[ti.n0 + c0 + i] : 0.0f;
+                    acc[16 * cb + i] = apply_act(acc[16 * cb + i] + b, p.act);
+                }
+                warp_store_rows<16>(stage, &acc[16 * cb], p.out + c0, row_off, lane);
             }
-            warp_store_rows<16>(stage, v, p.out + c0, row_off, lane);
         }
     }
 };
@@ -276,9 +285,16 @@ static int sm_count() {
     return n;
 }
 
+static int debug_flags() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PTGNN_TC_DEBUG"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 template <class Policy>
-static int launch_pipeline(const typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
+static int launch_pipeline(typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
     if (total_tiles <= 0) return PTGNN_OK;
+    p.dbg = debug_flags();
     static bool configured = false;
     if (!configured) {
         PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -1,0 +1,24 @@
+#!/bin/bash
+# timing experiments for the tcgen05 pipeline (results are wrong when PTGNN_TC_DEBUG != 0)
+for d in ${TC_DEBUG_LIST:-0 4 7 15}; do
+  echo "== PTGNN_TC_DEBUG=$d"
+  PTGNN_TC_DEBUG=$d timeout -s KILL 200 python - <<'PY'
+import torch, sys, os
+sys.path.insert(0, os.getcwd())
+import bench
+import ptgnn_b200 as P
+from ptgnn_b200 import _native as N
+batch = bench.make_batch("graph2class")
+gnn = bench.build_model(17, "sum").cuda()
+h = torch.randn(batch.num_nodes, 128).cuda()
+adj = [(s.cuda(), t.cuda()) for s, t in batch.adjacency_lists]
+ident = torch.arange(batch.num_nodes, device="cuda")
+ex = list(adj) + [(t, s) for s, t in adj] + [(ident, ident)]
+with torch.no_grad():
+    for _ in range(2): gnn.gnn(h, ex, None, None, {}, {})
+    N.kernel_timing(True); N.read_kernel_timing()
+    for _ in range(3): gnn.gnn(h, ex, None, None, {}, {})
+    kt = N.read_kernel_timing()
+print({k: round(v[0] / max(v[1], 1), 4) for k, v in kt.items() if v[1]})
+PY
+done
