@@ -103,6 +103,32 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- L2 residency control ---------------------------------------------------------------------------------------
+// The per-layer working set (messages 566 MB written + read once) streams through a 126 MB L2 that would otherwise
+// keep the 105 MB of node states every gather hits: messages are tagged evict-first, gathered state rows evict-last.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst_smem, const void *src, uint64_t policy) {   // full 16 bytes
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "l"(policy));
+}
+__device__ __forceinline__ void st_f4_hint(float *p, const float4 &v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+__device__ __forceinline__ float4 ld_stream_f4_hint(const float4 *p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
+
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {  // read-once data: do not allocate in L1
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

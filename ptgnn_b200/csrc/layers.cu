@@ -437,7 +437,7 @@ extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, const float 
                                   st);
     }
     if (rc) return rc;
-    ReduceEpilogue epi{message_activation, ln_weight, ln_bias, ln_eps};
+    ReduceEpilogue epi{0, message_activation, ln_weight, ln_bias, ln_eps};
     rc = launch_segment_reduce(msg, row_ptr, nullptr, num_nodes, E, D, reduce, y, nullptr, &epi, st);
     if (rc) return rc;
     if (!dense_weight) return PTGNN_OK;

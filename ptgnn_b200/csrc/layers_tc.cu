@@ -61,23 +61,28 @@ __global__ void split_weights_kernel(const __grid_constant__ SplitSrc s, float *
         lo[i] = x - h;
     }
 }
-// P1[jb][n][k] = weight_ih[(n/32)*H + jb*32 + n%32][k], P2 likewise from weight_hh (n in [0,96): gates r, z, n)
+// Gate-blocked GRU weights, 32 hidden units per block jb, 128 rows per block so that ONE N = 128 MMA per K-step serves
+// both GEMMs of the cell (tcgen05 instructions cost ~100 cycles regardless of N: fewer, wider MMAs win over exact N):
+//   P1[jb][n][k], n in [0,128):  [W_ir ; W_iz ; W_in ; 0   ]   (weight_ih rows, k < D)   accumulator cols r | z | i_n | h_n
+//   P2[jb][n][k], n in [0,128):  [W_hr ; W_hz ; 0    ; W_hn]   (weight_hh rows, k < H)
+// The zero blocks make the input GEMM clear the h_n columns and leave i_n untouched by the hidden GEMM.
 __global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh, int H, int D,
                                       float *__restrict__ p1_hi, float *__restrict__ p1_lo, float *__restrict__ p2_hi,
                                       float *__restrict__ p2_lo) {
     const int nblk = H / 32;
-    const int64_t n1 = (int64_t)nblk * 96 * D, n2 = (int64_t)nblk * 96 * H;
+    const int64_t n1 = (int64_t)nblk * 128 * D, n2 = (int64_t)nblk * 128 * H;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
-        float x;
         if (i < n1) {
-            const int k = (int)(i % D), n = (int)((i / D) % 96), jb = (int)(i / ((int64_t)96 * D));
-            x = w_ih[(size_t)((n / 32) * H + jb * 32 + n % 32) * D + k];
+            const int k = (int)(i % D), n = (int)((i / D) % 128), jb = (int)(i / ((int64_t)128 * D));
+            const int gate = n / 32;   // 0 r, 1 z, 2 i_n, 3 zero
+            const float x = gate < 3 ? w_ih[(size_t)(gate * H + jb * 32 + n % 32) * D + k] : 0.0f;
             const float h = tf32_hi(x);
             p1_hi[i] = h; p1_lo[i] = x - h;
         } else {
             const int64_t r = i - n1;
-            const int k = (int)(r % H), n = (int)((r / H) % 96), jb = (int)(r / ((int64_t)96 * H));
-            x = w_hh[(size_t)((n / 32) * H + jb * 32 + n % 32) * H + k];
+            const int k = (int)(r % H), n = (int)((r / H) % 128), jb = (int)(r / ((int64_t)128 * H));
+            const int gate = n / 32;   // 0 r, 1 z, 2 zero, 3 h_n
+            const float x = gate == 2 ? 0.0f : w_hh[(size_t)((gate == 3 ? 2 : gate) * H + jb * 32 + n % 32) * H + k];
             const float h = tf32_hi(x);
             p2_hi[r] = h; p2_lo[r] = x - h;
         }
@@ -94,6 +99,8 @@ struct MsgPolicy {
         const int32_t *src32, *tgt32, *pos;
         float *msg;
         int H, D, Kw, use_target, num_types, n_blocks, dbg;
+        unsigned long long *trace;
+        int hints;   // L2 residency hints: 1 = gathers evict-last, 2 = message stores evict-first
         int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
         int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
     };
@@ -132,14 +139,13 @@ struct MsgPolicy {
     }
     // warp `half` owns accumulator columns [64*half, 64*half + 64)
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
-        const int c0 = 64 * half;
-        if (c0 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0, &acc[0]);
-        if (c0 + 32 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0 + 32, &acc[32]);
+        tmem_drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], int quarter, int half, int lane, float *stage) {
+    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
         const int e = ti.e0 + quarter * 32 + lane;
-        long long row_off = -1;
-        if (e < ti.e_end) row_off = (long long)p.pos[e] * p.D + ti.n0;
+        return e < ti.e_end ? (long long)p.pos[e] * p.D + ti.n0 : -1;
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off, int half, int lane, float *stage) {
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
             const int c0 = 64 * half + 32 * cb;
@@ -155,11 +161,13 @@ struct MsgPolicy {
 struct GruPolicy {
     struct Params {
         CUtensorMap map_agg, map_h;                              // [N, D], [N, H], box {32, 128}
-        CUtensorMap map_p1_hi, map_p1_lo, map_p2_hi, map_p2_lo;  // [n_jb*96, D] / [n_jb*96, H], box {32, 96}
+        CUtensorMap map_p1_hi, map_p1_lo, map_p2_hi, map_p2_lo;  // [n_jb*128, D] / [n_jb*128, H], box {32, 128}
         const float *h;
         const float *b_ih, *b_hh;
         float *out;
         int num_nodes, H, D, n_jb, dbg;
+        unsigned long long *trace;
+        int hints;   // L2 residency hints: 1 = gathers evict-last, 2 = message stores evict-first
     };
     struct Tile { int row0, jb; };
 
@@ -171,7 +179,7 @@ struct GruPolicy {
     __device__ static int num_segments(const Params &, const Tile &) { return 2; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
         Segment s;
-        s.a = nullptr; s.lda = 0; s.a_row0 = ti.row0; s.b_row0 = ti.jb * 96; s.b_col0 = 0; s.b_box_rows = 96;
+        s.a = nullptr; s.lda = 0; s.a_row0 = ti.row0; s.b_row0 = ti.jb * 128; s.b_col0 = 0; s.b_box_rows = 128;
         if (seg == 0) {
             s.a_map = &p.map_agg; s.K = p.D; s.b_hi_map = &p.map_p1_hi; s.b_lo_map = &p.map_p1_lo;
         } else {
@@ -184,25 +192,23 @@ struct GruPolicy {
         return row < p.num_nodes ? row : -1;
     }
     __device__ static int mma_groups(const Params &, const Tile &, int seg, MmaGroup (&g)[2]) {
-        if (seg == 0) {  // [r z i_n] = agg x W_i{r,z,n}^T
-            g[0] = MmaGroup{96, 0, 0, true};
-            return 1;
-        }
-        g[0] = MmaGroup{64, 0, 0, false};   // [r z] += h x W_h{r,z}^T
-        g[1] = MmaGroup{32, 64, 96, true};  // h_n   = h x W_hn^T
-        return 2;
+        // seg 0: [r z i_n h_n] = agg x [W_ir W_iz W_in 0]^T (fresh);  seg 1: += h x [W_hr W_hz 0 W_hn]^T
+        g[0] = MmaGroup{128, 0, 0, seg == 0};
+        return 1;
     }
     // accumulator columns: [0,32) r | [32,64) z | [64,96) i_n | [96,128) h_n (pre-activations without biases);
     // warp `half` owns hidden units j0 + 16*half .. +16 and therefore 16 columns of each gate group
     __device__ static void drain(const Params &, const Tile &, uint32_t tmem_lane, int half, float (&acc)[64]) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld_sum16(tmem_lane + 32 * g + 16 * half, &acc[16 * g]);
+        tmem_drain_4x16(tmem_lane, 16 * half, acc);
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], int quarter, int half, int lane, float *stage) {
+    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
         const int row = ti.row0 + quarter * 32 + lane;
+        return row < p.num_nodes ? (long long)row * p.H + ti.jb * 32 : -1;
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off0, int half, int lane, float *stage) {
         const int H = p.H;
         const int j0 = ti.jb * 32 + 16 * half;
-        const long long row_off = row < p.num_nodes ? (long long)row * H + j0 : -1;
+        const long long row_off = row_off0 < 0 ? -1 : row_off0 + 16 * half;
         float hval[16];
         warp_load_rows<16>(stage, hval, p.h, row_off, lane);   // h[row][j0 .. j0+16), coalesced
 #pragma unroll
@@ -226,6 +232,8 @@ struct DensePolicy {
         const float *bias;
         float *out;
         int num_nodes, D, Hout, act, n_blocks, dbg;
+        unsigned long long *trace;
+        int hints;   // L2 residency hints: 1 = gathers evict-last, 2 = message stores evict-first
     };
     struct Tile { int row0, n0, b_rows; };
 
@@ -251,13 +259,13 @@ struct DensePolicy {
         return 1;
     }
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
-        const int c0 = 64 * half;
-        if (c0 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0, &acc[0]);
-        if (c0 + 32 < ti.b_rows) tmem_ld_sum32(tmem_lane + c0 + 32, &acc[32]);
+        tmem_drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], int quarter, int half, int lane, float *stage) {
+    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
         const int row = ti.row0 + quarter * 32 + lane;
-        const long long row_off = row < p.num_nodes ? (long long)row * p.Hout + ti.n0 : -1;
+        return row < p.num_nodes ? (long long)row * p.Hout + ti.n0 : -1;
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off, int half, int lane, float *stage) {
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
             const int c0 = 64 * half + 16 * cb;
@@ -285,32 +293,68 @@ static int sm_count() {
     return n;
 }
 
+int l2_hint_flags() {   // PTGNN_L2_HINTS bitmask (default 0; measured: no gain on B200): 4 = reduce loads with L2 evict-first
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PTGNN_L2_HINTS"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 static int debug_flags() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("PTGNN_TC_DEBUG"); v = e ? atoi(e) : 0; }
     return v;
 }
 
-template <class Policy>
-static int launch_pipeline(typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
-    if (total_tiles <= 0) return PTGNN_OK;
-    p.dbg = debug_flags();
+// Operand staging mode per kernel (see Mode<> in tc_pipeline.cuh); PTGNN_TC_MODE=ss|ts overrides the default for A/B runs.
+static int mode_override() {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("PTGNN_TC_MODE");
+        v = !e ? -1 : (e[0] == 't' ? 1 : 0);
+    }
+    return v;
+}
+
+// PTGNN_TC_TRACE=<category>: timeline trace of CTA 0 for launches of that kernel category; read it back with
+// ptgnn_b200_debug_trace() (debug only, not part of the public header).
+static unsigned long long *g_trace_dev = nullptr;
+static unsigned long long *trace_buffer(int category) {
+    static int want = -2;
+    if (want == -2) { const char *e = getenv("PTGNN_TC_TRACE"); want = e ? atoi(e) : -1; }
+    if (want != category) return nullptr;
+    if (!g_trace_dev) { if (cudaMalloc(&g_trace_dev, 3 * 2048 * 8) != cudaSuccess) return nullptr; }
+    cudaMemset(g_trace_dev, 0, 3 * 2048 * 8);
+    return g_trace_dev;
+}
+
+template <class Policy, bool TS>
+static int launch_mode(typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_kernel<Policy, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mode<TS>::SMEM_BYTES));
         configured = true;
     }
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
     {
         TimedScope timed__(category, st);
-        tc_pipeline_kernel<Policy><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+        tc_pipeline_kernel<Policy, TS><<<grid, NUM_THREADS, Mode<TS>::SMEM_BYTES, st>>>(p);
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
 }
 
+template <class Policy>
+static int launch_pipeline(typename Policy::Params &p, int total_tiles, int category, bool ts_default, cudaStream_t st) {
+    if (total_tiles <= 0) return PTGNN_OK;
+    p.dbg = debug_flags();
+    p.trace = trace_buffer(category);
+    p.hints = l2_hint_flags();
+    const bool ts = mode_override() < 0 ? ts_default : mode_override() == 1;
+    return ts ? launch_mode<Policy, true>(p, total_tiles, category, st) : launch_mode<Policy, false>(p, total_tiles, category, st);
+}
+
 size_t split_edge_weights_bytes(int num_types, int D, int Kw) { return 2 * ws_slice((size_t)num_types * D * Kw, 4); }
-size_t gru_pack_bytes(int H, int D) { return 2 * ws_slice((size_t)(H / 32) * 96 * D, 4) + 2 * ws_slice((size_t)(H / 32) * 96 * H, 4); }
+size_t gru_pack_bytes(int H, int D) { return 2 * ws_slice((size_t)(H / 32) * 128 * D, 4) + 2 * ws_slice((size_t)(H / 32) * 128 * H, 4); }
 size_t dense_split_bytes(int Hout, int D) { return 2 * ws_slice((size_t)Hout * D, 4); }
 
 bool supported_message(int H, int D) { return H % 4 == 0 && D % 16 == 0 && H >= 32 && D >= 16; }
@@ -345,13 +389,13 @@ int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_
         tiles += (int)ceil_div(type_off[t + 1] - type_off[t], TILE_M);
     }
     for (int t = num_types; t <= PTGNN_MAX_EDGE_TYPES; ++t) { p.edge_off[t] = (int32_t)type_off[num_types]; p.tile_off[t] = tiles; }
-    return launch_pipeline<MsgPolicy>(p, tiles * p.n_blocks, PTGNN_KERNEL_MESSAGE, st);
+    return launch_pipeline<MsgPolicy>(p, tiles * p.n_blocks, PTGNN_KERNEL_MESSAGE, true, st);
 }
 
 int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D, const float *w_ih, const float *w_hh,
                const float *b_ih, const float *b_hh, float *out, void *scratch, cudaStream_t st) {
     char *s = static_cast<char *>(scratch);
-    const size_t s1 = ws_slice((size_t)(H / 32) * 96 * D, 4), s2 = ws_slice((size_t)(H / 32) * 96 * H, 4);
+    const size_t s1 = ws_slice((size_t)(H / 32) * 128 * D, 4), s2 = ws_slice((size_t)(H / 32) * 128 * H, 4);
     float *p1_hi = reinterpret_cast<float *>(s), *p1_lo = reinterpret_cast<float *>(s + s1);
     float *p2_hi = reinterpret_cast<float *>(s + 2 * s1), *p2_lo = reinterpret_cast<float *>(s + 2 * s1 + s2);
     {
@@ -360,18 +404,18 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
     }
     PTGNN_LAUNCHED();
     GruPolicy::Params p{};
-    const uint64_t prow = (uint64_t)(H / 32) * 96;
+    const uint64_t prow = (uint64_t)(H / 32) * 128;
     int rc = make_map_2d(&p.map_agg, agg, num_nodes, D, D, 128);
     if (!rc) rc = make_map_2d(&p.map_h, h, num_nodes, H, H, 128);
-    if (!rc) rc = make_map_2d(&p.map_p1_hi, p1_hi, prow, D, D, 96);
-    if (!rc) rc = make_map_2d(&p.map_p1_lo, p1_lo, prow, D, D, 96);
-    if (!rc) rc = make_map_2d(&p.map_p2_hi, p2_hi, prow, H, H, 96);
-    if (!rc) rc = make_map_2d(&p.map_p2_lo, p2_lo, prow, H, H, 96);
+    if (!rc) rc = make_map_2d(&p.map_p1_hi, p1_hi, prow, D, D, 128);
+    if (!rc) rc = make_map_2d(&p.map_p1_lo, p1_lo, prow, D, D, 128);
+    if (!rc) rc = make_map_2d(&p.map_p2_hi, p2_hi, prow, H, H, 128);
+    if (!rc) rc = make_map_2d(&p.map_p2_lo, p2_lo, prow, H, H, 128);
     if (rc) return rc;
     p.h = h; p.b_ih = b_ih; p.b_hh = b_hh;
     p.out = out; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = H / 32;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_jb;
-    return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, st);
+    return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, true, st);
 }
 
 int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const float *bias, int Hout, int act, float *out,
@@ -393,8 +437,16 @@ int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const
     p.bias = bias; p.out = out; p.num_nodes = (int)num_nodes; p.D = D; p.Hout = Hout;
     p.act = act; p.n_blocks = (Hout + 127) / 128;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_blocks;
-    return launch_pipeline<DensePolicy>(p, tiles, PTGNN_KERNEL_DENSE, st);
+    return launch_pipeline<DensePolicy>(p, tiles, PTGNN_KERNEL_DENSE, true, st);
 }
 
 }  // namespace tc
 }  // namespace ptgnn
+
+// debug only: copies the last timeline trace (3 x 2048 uint64) to `out`; returns 0 if tracing is off
+extern "C" int ptgnn_b200_debug_trace(unsigned long long *out) {
+    if (!ptgnn::tc::g_trace_dev) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, ptgnn::tc::g_trace_dev, 3 * 2048 * 8, cudaMemcpyDeviceToHost);
+    return 1;
+}

@@ -5,6 +5,7 @@
 namespace ptgnn {
 namespace tc {
 
+int l2_hint_flags();
 bool supported_message(int H, int D);
 bool supported_gru(int H, int D);
 bool supported_dense(int D, int Hout);

@@ -17,6 +17,7 @@
 namespace ptgnn {
 
 struct ReduceEpilogue {
+    int hint;            // != 0: read the message rows with an L2 evict-first policy (they are dead afterwards)
     int act;             // PTGNN_ACT_* applied to the aggregated row
     const float *ln_w;   // LayerNorm weight/bias (nullptr = no LayerNorm)
     const float *ln_b;
@@ -203,6 +204,7 @@ segment_reduce_stream_kernel(const float *__restrict__ msg, const int32_t *__res
     const size_t ld4 = (size_t)D / 4;
     const float4 *msg4 = reinterpret_cast<const float4 *>(msg);
     float4 *out4 = reinterpret_cast<float4 *>(out);
+    const uint64_t evict_first = l2_policy_evict_first();   // message rows are dead after this read
 
     int cur = 0;                                                    // row being accumulated (index inside the warp's block)
     int cur_end = __shfl_sync(0xffffffffu, bound, 1);
@@ -277,7 +279,8 @@ segment_reduce_stream_kernel(const float *__restrict__ msg, const int32_t *__res
                 const size_t row = perm != nullptr ? (size_t)__shfl_sync(0xffffffffu, my_row, u) : (size_t)(j + u);
 #pragma unroll
                 for (int c = 0; c < CHUNKS; ++c)
-                    if (col_ok[c]) m[u][c] = ld_stream_f4(msg4 + row * ld4 + c * 32 + lane);
+                    if (col_ok[c]) m[u][c] = epi.hint ? ld_stream_f4_hint(msg4 + row * ld4 + c * 32 + lane, evict_first)
+                                                      : ld_stream_f4(msg4 + row * ld4 + c * 32 + lane);
             }
         }
 #pragma unroll

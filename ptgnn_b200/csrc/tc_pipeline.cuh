@@ -10,7 +10,7 @@
 //                         hi*lo + lo*hi into the CORRECTION accumulator (tensor-core accumulation truncates, so the
 //                         small terms must not perturb the main sum); tcgen05.commit -> empty[slot]; per tile
 //                         commit -> tmem_full.
-//   warps 5-12 EPILOGUE   wait tmem_full; drain main + correction into registers (row per thread, two warps per TMEM
+//   warps 8-15 EPILOGUE   wait tmem_full; drain main + correction into registers (row per thread, two warps per TMEM
 //                         lane quarter, half of the columns each); release the accumulator (tmem_empty) BEFORE the
 //                         policy's store phase (smem-transposed coalesced rows), so the next tile's MMAs overlap it.
 //
@@ -32,7 +32,8 @@
 //   __device__ static int  mma_groups(const Params&, const Tile&, int seg, MmaGroup (&g)[2]);
 //   __device__ static void drain(const Params&, const Tile&, uint32_t tmem_lane, int half, float (&acc)[64]);
 //                          (read this warp's share of main + correction accumulators; tmem_ld_sum16/32 below)
-//   __device__ static void store(const Params&, const Tile&, float (&acc)[64], int quarter, int half, int lane, float* stage);
+//   __device__ static long long store_row_offset(const Params&, const Tile&, int quarter, int lane);   (-1 = row not stored)
+//   __device__ static void store(const Params&, const Tile&, float (&acc)[64], long long row_off, int half, int lane, float* stage);
 #pragma once
 #include <cuda.h>
 
@@ -43,21 +44,37 @@ namespace tc {
 
 constexpr int TILE_M = 128;
 constexpr int CHUNK_K = 32;                       // fp32 per k-chunk = one 128-byte swizzled row
-constexpr int NUM_SLOTS = 4;
-constexpr int LOOKAHEAD = 2;                      // chunks of loads in flight ahead of the chunk being converted; with 4 slots the
-                                                  // producer then waits on the MMA of chunk c-2, not c-1: one iteration of slack
-                                                  // takes the arrive->commit->wake handshake (~0.5 us) off the critical path
-constexpr int PRODUCER_THREADS = 128;
+// Warp roles, in warpgroups of 4 so that setmaxnreg can move registers from the light roles to the epilogue:
+//   WG0 = warps 0-3 producers (120 regs) | WG1 = warp 4 MMA issuer, warps 5-7 idle (40) | WG2+WG3 = warps 8-15 epilogue (176)
+constexpr int NUM_PRODUCER_WARPS = 4;
+constexpr int PRODUCER_THREADS = NUM_PRODUCER_WARPS * 32;
 constexpr int MMA_WARP = 4;
+constexpr int FIRST_EPI_WARP = 8;
 constexpr int NUM_EPI_WARPS = 8;                  // two per TMEM lane quarter, each draining half of the columns
-constexpr int NUM_THREADS = (5 + NUM_EPI_WARPS) * 32;
+constexpr int NUM_THREADS = 16 * 32;
+constexpr int PRODUCER_REGS = 120, MMA_REGS = 40, EPI_REGS = 176;   // (120 + 40 + 176 + 176) * 128 = 65536
 constexpr int OPERAND_BYTES = TILE_M * CHUNK_K * 4;   // 16 KB: one 128 x 32 fp32 operand tile
-constexpr int SLOT_BYTES = 3 * OPERAND_BYTES;         // raw A | B_hi | B_lo
-constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
 constexpr int STAGE_BYTES_PER_WARP = 32 * 32 * 4;     // epilogue transpose buffer: 32 rows x 32 fp32
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
-constexpr int CORR_OFF = 128;                         // correction accumulator columns
-constexpr int A_TMEM_OFF = 256;                       // A operand ring: slot s at columns A_TMEM_OFF + 64 s (hi | lo)
+constexpr int CORR_OFF = 128;                         // correction accumulator columns (relative to the main ones)
+constexpr int A_TMEM_OFF = 256;                       // TS: A operand ring, slot s at columns A_TMEM_OFF + 64 s (hi | lo)
+
+// Two operand-staging modes (template parameter TS of the kernel):
+//   TS = true   A split into TMEM (tcgen05.st) -> MMAs read only B from shared memory; shared-memory ring 4 x 48 KB
+//               (raw A | B_hi | B_lo), loads issued 2 chunks ahead so the producer waits on the MMA of chunk c-2;
+//               TMEM = 256 accumulator columns (main + correction, single-buffered) + 256 columns of A.
+//   TS = false  A split in place in shared memory (A_hi | A_lo | B_hi | B_lo, ring 3 x 64 KB); TMEM = two accumulator
+//               sets of 256 columns, so the MMAs of tile i+1 overlap the whole epilogue of tile i.
+template <bool TS>
+struct Mode {
+    static constexpr int NUM_SLOTS = TS ? 4 : 3;
+    static constexpr int LOOKAHEAD = 2;
+    static constexpr int SLOT_BYTES = (TS ? 3 : 4) * OPERAND_BYTES;
+    static constexpr int B_HI_OFF = (TS ? 1 : 2) * OPERAND_BYTES;
+    static constexpr int B_LO_OFF = (TS ? 2 : 3) * OPERAND_BYTES;
+    static constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
+    static constexpr int NUM_ACC = TS ? 1 : 2;
+    static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
+};
 
 struct Segment {        // one K-range of the tile's GEMM
     const float *a;     // gathered A rows (row pitch lda) -- used when a_map == nullptr
@@ -85,10 +102,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
 
-// One lane polls the mbarrier, the warp re-converges on __syncwarp (32x fewer try_wait instructions on the XU pipe).
+// Whole-warp wait.  (Electing one lane to poll was measured to be slower: try_wait is a warp-level instruction
+// anyway, and the divergence/reconvergence around the elected loop adds latency to every hand-off.)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
+    (void)lane;
+    mbar_wait(bar, parity);
 }
 
 // ---- epilogue transposes through shared memory ---------------------------------------------------------------
@@ -96,8 +114,9 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, i
 // different 128-byte lines.  Staging 32 rows x NCOLS through a (chunk-XOR-swizzled) buffer lets each store
 // instruction write whole rows: 4 (NCOLS = 32) or 8 (NCOLS = 16) lines per instruction instead of 32.
 // `row_off` is this lane's destination element offset from `dst_base` (negative = row not stored).
-template <int NCOLS>
-__device__ __forceinline__ void warp_store_rows(float *stage, const float *v, float *dst_base, long long row_off, int lane) {
+template <int NCOLS, bool STREAM = false>
+__device__ __forceinline__ void warp_store_rows(float *stage, const float *v, float *dst_base, long long row_off, int lane,
+                                                uint64_t policy = 0) {
     constexpr int CPR = NCOLS / 4;   // 16-byte chunks per row
 #pragma unroll
     for (int j = 0; j < CPR; ++j)
@@ -109,7 +128,10 @@ __device__ __forceinline__ void warp_store_rows(float *stage, const float *v, fl
         const int idx = it * 32 + lane, row = idx / CPR, ch = idx % CPR;
         const float4 val = *reinterpret_cast<const float4 *>(stage + (row * CPR + (ch ^ (row & (CPR - 1)))) * 4);
         const long long off = __shfl_sync(0xffffffffu, row_off, row);
-        if (off >= 0) *reinterpret_cast<float4 *>(dst_base + off + ch * 4) = val;
+        if (off >= 0) {
+            if (STREAM) st_f4_hint(dst_base + off + ch * 4, val, policy);   // written once, read once: L2 evict-first
+            else *reinterpret_cast<float4 *>(dst_base + off + ch * 4) = val;
+        }
     }
     __syncwarp();
 }
@@ -134,31 +156,59 @@ __device__ __forceinline__ void warp_load_rows(float *stage, float *v, const flo
     __syncwarp();
 }
 
-// accumulator value = main + correction
-__device__ __forceinline__ void tmem_ld_sum32(uint32_t taddr, float *v) {
-    float m[32], c[32];
-    tmem_ld_32cols(taddr, m);
-    tmem_ld_32cols(taddr + CORR_OFF, c);
+// accumulator value = main + correction; all TMEM loads of a drain are issued before ONE wait
+// drain 64 consecutive columns [c0, c0+64) (only the 32-column blocks below `ncols`); two loads in flight per wait
+__device__ __forceinline__ void tmem_drain_2x32(uint32_t taddr, int c0, int ncols, float (&acc)[64]) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = m[i] + c[i];
+    for (int b = 0; b < 2; ++b) {
+        if (c0 + 32 * b < ncols) {   // warp-uniform
+            uint32_t m[32], c[32];
+            tmem_ld_32cols_async(taddr + c0 + 32 * b, m);
+            tmem_ld_32cols_async(taddr + c0 + 32 * b + CORR_OFF, c);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[32 * b + i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
+        }
+    }
 }
-__device__ __forceinline__ void tmem_ld_sum16(uint32_t taddr, float *v) {
-    float m[16], c[16];
-    tmem_ld_16cols(taddr, m);
-    tmem_ld_16cols(taddr + CORR_OFF, c);
+// drain 4 groups of 16 columns at taddr + 32 g + off (GRU gate groups); four loads in flight per wait
+__device__ __forceinline__ void tmem_drain_4x16(uint32_t taddr, int off, float (&acc)[64]) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = m[i] + c[i];
+    for (int gp = 0; gp < 2; ++gp) {
+        uint32_t m[2][16], c[2][16];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            tmem_ld_16cols_async(taddr + 32 * (2 * gp + g) + off, m[g]);
+            tmem_ld_16cols_async(taddr + 32 * (2 * gp + g) + off + CORR_OFF, c[g]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[16 * (2 * gp + g) + i] = __uint_as_float(m[g][i]) + __uint_as_float(c[g][i]);
+    }
 }
 
-template <class Policy>
+// Optional timeline trace (PTGNN_TC_TRACE): CTA 0 records %globaltimer at pipeline hand-offs, 3 roles x 2048 slots.
+struct Tracer {
+    unsigned long long *buf;
+    int n;
+    __device__ __forceinline__ void mark(int tag) {
+        if (buf != nullptr && n < 2048) { buf[n++] = (global_timer_ns() << 8) | (unsigned long long)(tag & 0xFF); }
+    }
+};
+
+template <class Policy, bool TS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __grid_constant__ typename Policy::Params p) {
+    using M = Mode<TS>;
+    constexpr int NUM_SLOTS = M::NUM_SLOTS, LOOKAHEAD = M::LOOKAHEAD, SLOT_BYTES = M::SLOT_BYTES, RING_BYTES = M::RING_BYTES;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned ring (SWIZZLE_128B descriptors / TMA swizzle assume base_offset = 0)
     unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + RING_BYTES);
     uint64_t *full = bars, *empty = bars + NUM_SLOTS, *landed = bars + 2 * NUM_SLOTS;
-    uint64_t *tmem_full = bars + 3 * NUM_SLOTS, *tmem_empty = bars + 3 * NUM_SLOTS + 1;
-    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 3 * NUM_SLOTS + 2);
+    uint64_t *tmem_full = bars + 3 * NUM_SLOTS, *tmem_empty = bars + 3 * NUM_SLOTS + 2;   // [NUM_ACC] each
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 3 * NUM_SLOTS + 4);
     float *stage_base = reinterpret_cast<float *>(ring + RING_BYTES + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,8 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             mbar_init(&empty[s], 1);                 // MMA commit: smem slot + TMEM A buffer may be overwritten
             mbar_init(&landed[s], 1);                // TMA bytes of this slot have landed
         }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, NUM_EPI_WARPS);
+        for (int a = 0; a < M::NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS); }
         mbar_init_fence();
     }
     if (warp == 0) tmem_alloc<512>(tmem_base_smem);
@@ -181,33 +230,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     // timing experiments only (PTGNN_TC_DEBUG; results are wrong when set): 1 = no MMAs, 2 = no loads, 4 = no stores,
     // 8 = no A conversion
     const int dbg = p.dbg;
+    unsigned long long *trace_base = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
 
-    if (warp < 4) {
+    if (warp < NUM_PRODUCER_WARPS) {
         // =========================================== PRODUCERS ===========================================
-        // copy mapping: lane l of warp w stages 16-byte chunk q = l & 7 of rows 32 w + (l >> 3) + 4 i (i < 8), i.e. every
-        // warp stages exactly the 32 rows it converts afterwards (only a __syncwarp between the two steps).
-        const int q = lane & 7, rsub = warp * 32 + (lane >> 3);
-        const int my_row = warp * 32 + lane;     // the row this thread converts (TMEM lane 32 * warp + lane)
+        // Warp w owns rows 32 w .. 32 w + 31.  It stages exactly the 16-byte pieces it converts afterwards: lane l -> piece
+        // q = l & 7 of rows r0 + (l >> 3) + 4 i, i < 8 (so only a __syncwarp separates staging and conversion), then
+        // thread `lane` converts row r0 + lane (all 32 floats of the chunk).
+        reg_dealloc<PRODUCER_REGS>();
+        const int quarter = warp;
+        const int q = lane & 7, rsub = quarter * 32 + (lane >> 3);
+        const int my_row = quarter * 32 + lane;
+        constexpr int PPT = 8;   // pieces per thread
         struct Cursor { int tile, seg, kc; };
-        typename Policy::Tile t_load, t_proc;
-        int rows_load[8];
-        Cursor cl{(int)blockIdx.x, 0, 0}, cp{(int)blockIdx.x, 0, 0};
-        bool load_valid = cl.tile < total_tiles, proc_valid = load_valid;
-        uint32_t c_load = 0, c_proc = 0;
-
-        auto load_rows = [&]() {
-            if (Policy::segment(p, t_load, cl.seg).a_map != nullptr) return;
+        typename Policy::Tile t_load, t_pref, t_proc;
+        Segment sg_load;
+        int rows_load[PPT], rows_pref[PPT];
+        const float *rowp[PPT];          // per (tile, segment): source pointer of this thread's pieces at k = 0 (nullptr = zero-fill)
+        uint32_t soff[PPT];              // swizzled shared-memory offsets of the pieces (constant per thread)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rows_load[i] = Policy::gather_row(p, t_load, cl.seg, rsub + 4 * i);
+        for (int i = 0; i < PPT; ++i) soff[i] = swz(rsub + 4 * i, q);
+        Cursor cl{(int)blockIdx.x, 0, 0}, cpf{(int)blockIdx.x, 0, 0}, cp{(int)blockIdx.x, 0, 0};
+        bool load_valid = cl.tile < total_tiles, pref_valid = false, proc_valid = load_valid;
+        uint32_t c_load = 0, c_proc = 0;
+        Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0};
+
+        // (tile, seg) that follows `c`; returns false past the end
+        auto advance_seg = [&](Cursor &c, typename Policy::Tile &t) -> bool {
+            ++c.seg;
+            c.kc = 0;
+            if (c.seg >= Policy::num_segments(p, t)) {
+                c.seg = 0;
+                c.tile += gridDim.x;
+                if (c.tile >= total_tiles) return false;
+                Policy::tile_setup(p, c.tile, t);
+            }
+            return true;
         };
-        if (load_valid) { Policy::tile_setup(p, cl.tile, t_load); load_rows(); }
+        auto fetch_rows = [&](const typename Policy::Tile &t, int seg, int (&rows)[PPT]) {
+            if (Policy::segment(p, t, seg).a_map != nullptr) return;
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) rows[i] = Policy::gather_row(p, t, seg, rsub + 4 * i);
+        };
+        auto set_row_pointers = [&]() {
+#pragma unroll
+            for (int i = 0; i < PPT; ++i)
+                rowp[i] = (sg_load.a_map == nullptr && rows_load[i] >= 0) ? sg_load.a + (size_t)rows_load[i] * sg_load.lda + q * 4 : nullptr;
+        };
+        if (load_valid) {
+            Policy::tile_setup(p, cl.tile, t_load);
+            sg_load = Policy::segment(p, t_load, 0);
+            fetch_rows(t_load, 0, rows_load);
+            set_row_pointers();
+            // gather indices of the NEXT (tile, segment) are fetched one step ahead: their ~1 us latency is off the path
+            t_pref = t_load; cpf = cl;
+            pref_valid = advance_seg(cpf, t_pref);
+            if (pref_valid) fetch_rows(t_pref, cpf.seg, rows_pref);
+        }
         if (proc_valid) Policy::tile_setup(p, cp.tile, t_proc);
 
         auto issue = [&]() {   // stage chunk (cl) into slot c_load % NUM_SLOTS
             const uint32_t slot = c_load % NUM_SLOTS, use = c_load / NUM_SLOTS;
-            mbar_wait_warp(&empty[slot], (use & 1) ^ 1, lane);
+            tr.mark(1);
+            mbar_wait(&empty[slot], (use & 1) ^ 1);
+            tr.mark(2);
             unsigned char *base = ring + slot * SLOT_BYTES;
-            const Segment sg = Policy::segment(p, t_load, cl.seg);
+            const Segment &sg = sg_load;
             const int kchunk = cl.kc * CHUNK_K;
             if (threadIdx.x == 0) {   // bulk tensor copies: weights (hi, lo) and, for contiguous rows, the raw A tile
                 if (dbg & 2) {
@@ -216,33 +304,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                     const uint32_t bytes = 2u * (uint32_t)sg.b_box_rows * 128u + (sg.a_map ? (uint32_t)OPERAND_BYTES : 0u);
                     mbar_expect_tx(&landed[slot], bytes);
                     if (sg.a_map) tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
-                    tma_load_2d(base + OPERAND_BYTES, sg.b_hi_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
-                    tma_load_2d(base + 2 * OPERAND_BYTES, sg.b_lo_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+                    tma_load_2d(base + M::B_HI_OFF, sg.b_hi_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+                    tma_load_2d(base + M::B_LO_OFF, sg.b_lo_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
                 }
             }
             if (sg.a_map == nullptr && !(dbg & 2)) {   // gathered rows
-                const int k0 = kchunk + q * 4;
-                const bool k_ok = k0 < sg.K;
+                const bool k_ok = kchunk + q * 4 < sg.K;
+                const uint32_t sbase = smem_u32(base);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int g = rows_load[i];
-                    const bool ok = k_ok && g >= 0;
-                    cp_async16(smem_u32(base + swz(rsub + 4 * i, q)),
-                               ok ? (const void *)(sg.a + (size_t)g * sg.lda + k0) : (const void *)sg.a, ok ? 16 : 0);
+                for (int i = 0; i < PPT; ++i) {
+                    const bool ok = k_ok && rowp[i] != nullptr;
+                    cp_async16(sbase + soff[i], ok ? (const void *)(rowp[i] + kchunk) : (const void *)sg.a, ok ? 16 : 0);
                 }
             }
             ++c_load;
             ++cl.kc;
-            if (cl.kc * CHUNK_K >= sg.K) {
-                cl.kc = 0;
-                ++cl.seg;
-                if (cl.seg >= Policy::num_segments(p, t_load)) {
-                    cl.seg = 0;
-                    cl.tile += gridDim.x;
-                    load_valid = cl.tile < total_tiles;
-                    if (load_valid) Policy::tile_setup(p, cl.tile, t_load);
+            if (cl.kc * CHUNK_K >= sg.K) {   // move to the prefetched (tile, segment) and prefetch the one after it
+                load_valid = pref_valid;
+                if (load_valid) {
+                    cl = cpf; t_load = t_pref;
+                    sg_load = Policy::segment(p, t_load, cl.seg);
+#pragma unroll
+                    for (int i = 0; i < PPT; ++i) rows_load[i] = rows_pref[i];
+                    set_row_pointers();
+                    pref_valid = advance_seg(cpf, t_pref);
+                    if (pref_valid) fetch_rows(t_pref, cpf.seg, rows_pref);
                 }
-                if (load_valid) load_rows();
             }
         };
 
@@ -251,56 +338,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             if (load_valid) issue();
             cp_async_commit();
         }
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        Segment sg_proc;
+        if (proc_valid) sg_proc = Policy::segment(p, t_proc, 0);
         while (proc_valid) {
             const uint32_t slot = c_proc % NUM_SLOTS, use = c_proc / NUM_SLOTS;
+            tr.mark(3);
             cp_async_wait<LOOKAHEAD - 1>();          // this thread's gathered pieces of chunk c_proc
-            __syncwarp();                            // ... and those of the other lanes of this warp (same 32 rows)
-            mbar_wait_warp(&landed[slot], use & 1, lane);   // TMA tiles of chunk c_proc
-            // convert this thread's row: 32 raw floats -> TF32 hi / lo -> TMEM columns of slot's A buffer
-            const unsigned char *base = ring + slot * SLOT_BYTES;
-            float hi[32], lo[32];
+            __syncwarp();                            // ... and those of the other lanes of this warp (same rows, same k-half)
+            tr.mark(4);
+            mbar_wait(&landed[slot], use & 1);       // TMA tiles of chunk c_proc
+            tr.mark(5);
+            unsigned char *base = ring + slot * SLOT_BYTES;
+            if constexpr (TS) {
+                // convert this thread's row: 32 raw floats -> TF32 hi / lo -> TMEM columns of the slot's A buffer
+                float hi[32], lo[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 v = *reinterpret_cast<const float4 *>(base + swz(my_row, j));
-                hi[4 * j] = tf32_hi(v.x); hi[4 * j + 1] = tf32_hi(v.y); hi[4 * j + 2] = tf32_hi(v.z); hi[4 * j + 3] = tf32_hi(v.w);
-                lo[4 * j] = v.x - hi[4 * j]; lo[4 * j + 1] = v.y - hi[4 * j + 1];
-                lo[4 * j + 2] = v.z - hi[4 * j + 2]; lo[4 * j + 3] = v.w - hi[4 * j + 3];
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = *reinterpret_cast<const float4 *>(base + swz(my_row, j));
+                    hi[4 * j] = tf32_hi(v.x); hi[4 * j + 1] = tf32_hi(v.y); hi[4 * j + 2] = tf32_hi(v.z); hi[4 * j + 3] = tf32_hi(v.w);
+                    lo[4 * j] = v.x - hi[4 * j]; lo[4 * j + 1] = v.y - hi[4 * j + 1];
+                    lo[4 * j + 2] = v.z - hi[4 * j + 2]; lo[4 * j + 3] = v.w - hi[4 * j + 3];
+                }
+                const uint32_t a_buf = tmem_lane + A_TMEM_OFF + slot * 64;
+                if (!(dbg & 8)) {
+                    tmem_st_32cols(a_buf, hi);
+                    tmem_st_32cols(a_buf + 32, lo);
+                    tmem_st_wait();
+                }
+                tc_fence_before_sync();
+            } else {
+                // in place: raw -> hi (same spot), lo (A_lo tile); the pieces this lane staged itself
+#pragma unroll
+                for (int i = 0; i < PPT; ++i) {
+                    float4 *ph = reinterpret_cast<float4 *>(base + swz(rsub + 4 * i, q));
+                    float4 *pl = reinterpret_cast<float4 *>(base + OPERAND_BYTES + swz(rsub + 4 * i, q));
+                    const float4 v = *ph;
+                    float4 hi, lo;
+                    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                    if (!(dbg & 8)) { *ph = hi; *pl = lo; }
+                }
+                fence_proxy_async_smem();
             }
-            const uint32_t a_buf = tmem_lane + A_TMEM_OFF + slot * 64;
-            if (!(dbg & 8)) {
-                tmem_st_32cols(a_buf, hi);
-                tmem_st_32cols(a_buf + 32, lo);
-                tmem_st_wait();
-            }
-            tc_fence_before_sync();
             mbar_arrive(&full[slot]);
+            tr.mark(6);
             ++c_proc;
             if (load_valid) issue();
             cp_async_commit();
-            const Segment sg = Policy::segment(p, t_proc, cp.seg);
             ++cp.kc;
-            if (cp.kc * CHUNK_K >= sg.K) {
-                cp.kc = 0;
-                ++cp.seg;
-                if (cp.seg >= Policy::num_segments(p, t_proc)) {
-                    cp.seg = 0;
-                    cp.tile += gridDim.x;
-                    proc_valid = cp.tile < total_tiles;
-                    if (proc_valid) Policy::tile_setup(p, cp.tile, t_proc);
-                }
+            if (cp.kc * CHUNK_K >= sg_proc.K) {
+                proc_valid = advance_seg(cp, t_proc);
+                if (proc_valid) sg_proc = Policy::segment(p, t_proc, cp.seg);
             }
         }
         cp_async_wait<0>();
-    } else if (warp == MMA_WARP) {
-        // =========================================== MMA ISSUER ===========================================
-        if (lane == 0) {
+    } else if (warp < FIRST_EPI_WARP) {
+        // =========================================== MMA ISSUER (warp 4; warps 5-7 only give their registers away) ========
+        reg_dealloc<MMA_REGS>();
+        if (warp == MMA_WARP && lane == 0) {
             uint32_t c = 0, tcount = 0;
+            Tracer tr{trace_base ? trace_base + 2048 : nullptr, 0};
             typename Policy::Tile t;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                tr.mark(10);
                 Policy::tile_setup(p, tile, t);
-                mbar_wait(tmem_empty, (tcount & 1) ^ 1);     // epilogue has drained the previous tile's accumulators
+                const uint32_t acc = tcount % M::NUM_ACC, acc_use = tcount / M::NUM_ACC;
+                tr.mark(11);
+                mbar_wait(&tmem_empty[acc], (acc_use & 1) ^ 1);   // the epilogue has drained this accumulator set
+                tr.mark(12);
                 tc_fence_after_sync();
+                const uint32_t tmem_acc = tmem_base + acc * 256;
                 const int nseg = Policy::num_segments(p, t);
                 for (int seg = 0; seg < nseg; ++seg) {
                     const Segment sg = Policy::segment(p, t, seg);
@@ -309,52 +417,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                     const int nkc = (sg.K + CHUNK_K - 1) / CHUNK_K;
                     for (int kc = 0; kc < nkc; ++kc, ++c) {
                         const uint32_t slot = c % NUM_SLOTS, use = c / NUM_SLOTS;
+                        tr.mark(13);
                         mbar_wait(&full[slot], use & 1);
+                        tr.mark(14);
                         tc_fence_after_sync();
                         const uint32_t base = smem_u32(ring + slot * SLOT_BYTES);
                         const uint32_t a_buf = tmem_base + A_TMEM_OFF + slot * 64;
                         const int kvalid = min(CHUNK_K, sg.K - kc * CHUNK_K);
-                        const int ksteps = (kvalid + 7) / 8;
-                        for (int ks = 0; ks < ksteps && !(dbg & 1); ++ks) {
-                            const uint32_t a_hi = a_buf + ks * 8, a_lo = a_buf + 32 + ks * 8;
-                            for (int gi = 0; gi < ng; ++gi) {
-                                const uint64_t b_hi = make_smem_desc_sw128(base + OPERAND_BYTES + g[gi].row_off * 128 + ks * 32);
-                                const uint64_t b_lo = make_smem_desc_sw128(base + 2 * OPERAND_BYTES + g[gi].row_off * 128 + ks * 32);
+                        const int ksteps = (dbg & 1) ? 0 : (kvalid + 7) / 8;
+                        // descriptors of K-step 0; later K-steps are +32 bytes (= +2 in the 16-byte address field) / +8 TMEM
+                        // columns, added as immediates in the unrolled loop (the issue rate of this one thread is the limit)
+                        const uint64_t sa_hi0 = make_smem_desc_sw128(base), sa_lo0 = make_smem_desc_sw128(base + OPERAND_BYTES);
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+                            if (gi < ng) {
+                                const uint64_t b_hi0 = make_smem_desc_sw128(base + M::B_HI_OFF + g[gi].row_off * 128);
+                                const uint64_t b_lo0 = make_smem_desc_sw128(base + M::B_LO_OFF + g[gi].row_off * 128);
                                 const uint32_t idesc = make_instr_desc(FMT_TF32, TILE_M, (uint32_t)g[gi].n);
-                                const uint32_t d_main = tmem_base + g[gi].col_off;
-                                const uint32_t d_corr = d_main + CORR_OFF;
-                                const bool first = g[gi].fresh && kc == 0 && ks == 0;
-                                mma_tf32_ts(d_main, a_hi, b_hi, idesc, first ? 0u : 1u);
-                                mma_tf32_ts(d_corr, a_hi, b_lo, idesc, first ? 0u : 1u);
-                                mma_tf32_ts(d_corr, a_lo, b_hi, idesc, 1u);
+                                const uint32_t d_main = tmem_acc + g[gi].col_off, d_corr = d_main + CORR_OFF;
+                                const uint32_t acc0 = (g[gi].fresh && kc == 0) ? 0u : 1u;
+#pragma unroll
+                                for (int ks = 0; ks < CHUNK_K / 8; ++ks) {
+                                    if (ks < ksteps) {
+                                        const uint32_t first = ks == 0 ? acc0 : 1u;
+                                        if constexpr (TS) {
+                                            mma_tf32_ts(d_main, a_buf + ks * 8, b_hi0 + ks * 2, idesc, first);
+                                            mma_tf32_ts(d_corr, a_buf + ks * 8, b_lo0 + ks * 2, idesc, first);
+                                            mma_tf32_ts(d_corr, a_buf + 32 + ks * 8, b_hi0 + ks * 2, idesc, 1u);
+                                        } else {
+                                            mma_tf32_ss(d_main, sa_hi0 + ks * 2, b_hi0 + ks * 2, idesc, first);
+                                            mma_tf32_ss(d_corr, sa_hi0 + ks * 2, b_lo0 + ks * 2, idesc, first);
+                                            mma_tf32_ss(d_corr, sa_lo0 + ks * 2, b_hi0 + ks * 2, idesc, 1u);
+                                        }
+                                    }
+                                }
                             }
                         }
                         mma_commit(&empty[slot]);
+                        tr.mark(15);
                     }
                 }
-                mma_commit(tmem_full);
+                mma_commit(&tmem_full[acc]);
             }
         }
         __syncwarp();
     } else {
         // =========================================== EPILOGUE ===========================================
-        const int ew = warp - 5;                 // 0..7
+        reg_alloc<EPI_REGS>();
+        const int ew = warp - FIRST_EPI_WARP;    // 0..7
         const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 are the ones this warp may read
         const int half = ew >> 2;                // which half of the accumulator columns this warp drains
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float *stage = stage_base + ew * (STAGE_BYTES_PER_WARP / 4);
         uint32_t tcount = 0;
+        Tracer tr{(trace_base && ew == 0 && lane == 0) ? trace_base + 4096 : nullptr, 0};
         typename Policy::Tile t;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             Policy::tile_setup(p, tile, t);
-            mbar_wait_warp(tmem_full, tcount & 1, lane);
+            const long long row_off = Policy::store_row_offset(p, t, quarter, lane);   // issued before the wait: latency hidden
+            const uint32_t aset = tcount % M::NUM_ACC, aset_use = tcount / M::NUM_ACC;
+            tr.mark(20);
+            mbar_wait_warp(&tmem_full[aset], aset_use & 1, lane);
+            tr.mark(21);
             tc_fence_after_sync();
             float acc[64];
-            Policy::drain(p, t, tmem_lane, half, acc);
+            Policy::drain(p, t, tmem_lane + aset * 256, half, acc);
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);          // the next tile's MMAs may start while we store
-            if (!(dbg & 4)) Policy::store(p, t, acc, quarter, half, lane, stage);
+            if (lane == 0) mbar_arrive(&tmem_empty[aset]);   // this accumulator set may be overwritten while we store
+            tr.mark(22);
+            if (!(dbg & 4)) Policy::store(p, t, acc, row_off, half, lane, stage);
+            tr.mark(23);
         }
     }
     tc_fence_before_sync();

@@ -1,13 +1,10 @@
 #!/bin/bash
-# timing experiments for the tcgen05 pipeline (results are wrong when PTGNN_TC_DEBUG != 0)
-for m in ${TC_MODE_LIST:-ts ss}; do
-for d in ${TC_DEBUG_LIST:-0 4 7 15}; do
-  echo "== PTGNN_TC_MODE=$m PTGNN_TC_DEBUG=$d"
-  PTGNN_TC_MODE=$m PTGNN_TC_DEBUG=$d timeout -s KILL 200 python - <<'PY'
+for hm in 0 1 2 4 7; do
+  echo "== PTGNN_L2_HINTS=$hm"
+  PTGNN_L2_HINTS=$hm timeout -s KILL 200 python - <<'PY' 2>&1 | tail -2
 import torch, sys, os
 sys.path.insert(0, os.getcwd())
 import bench
-import ptgnn_b200 as P
 from ptgnn_b200 import _native as N
 batch = bench.make_batch("graph2class")
 gnn = bench.build_model(17, "sum").cuda()
@@ -22,5 +19,4 @@ with torch.no_grad():
     kt = N.read_kernel_timing()
 print({k: round(v[0] / max(v[1], 1), 4) for k, v in kt.items() if v[1]})
 PY
-done
 done
