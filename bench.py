@@ -41,6 +41,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    return 1400.0
+
+
+# DRAM traffic per launch (read + write bytes) of the kernels from the committed ncu --set full capture
+# (profiles/r01_final_*.md); None when no capture of the current kernel exists.
+NCU_TRAFFIC = {"message": 943.8e6, "reduce": 620.6e6, "gru": 289.3e6}   # profiles/r01_final_kernels.md (config 2, sum)
+
+
 def usable_cores() -> int:
     """Host cores this process may actually use: min(affinity mask, cgroup CPU quota)."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -345,28 +358,41 @@ def main():
     kt = N.read_kernel_timing()
     N.kernel_timing(False)
     peak, peak_src = measured_peaks()
+    tensor_peak = measured_tensor_peak()
     D = HIDDEN
-    alg_bytes = {  # per launch, see DESIGN.md "algorithmic bytes"
+    alg_bytes = {  # per launch, see DESIGN.md section 3 ("alg. bytes")
         "message": n_nodes * HIDDEN * 4 + E * (D * 4 + 8),
         "reduce": E * D * 4 + (n_nodes + 1) * 4 + n_nodes * D * 4,
         "gru": n_nodes * D * 4 + 2 * n_nodes * HIDDEN * 4 + 6 * HIDDEN * HIDDEN * 4,
     }
+    alg_flops = {  # fp32 multiply-adds the reference performs (x2); the 3xTF32 path issues 3x this on the tensor cores
+        "message": 2 * E * HIDDEN * D,
+        "gru": 2 * n_nodes * (3 * HIDDEN * D + 3 * HIDDEN * HIDDEN),
+    }
+    kernel_names = {"message": "tc_pipeline_kernel<MsgPolicy> (edge messages)", "reduce": "segment_reduce_stream_kernel",
+                    "gru": "tc_pipeline_kernel<GruPolicy> (GRUCell update)", "plan": "edge-plan kernels", "pack": "weight split/pack"}
     kernels = {}
     for name, (ms, cnt) in kt.items():
         if cnt:
             avg_ms = ms / cnt
-            entry = {"avg_ms": avg_ms, "launches_per_step": cnt / ksteps, "share_of_step": ms / ksteps / ms_step}
+            entry = {"kernel": kernel_names.get(name, name), "avg_ms": avg_ms, "launches_per_step": cnt / ksteps,
+                     "share_of_step": ms / ksteps / ms_step}
             if name in alg_bytes:
                 entry["alg_bytes"] = alg_bytes[name]
                 entry["achieved_gbs"] = alg_bytes[name] / (avg_ms * 1e-3) / 1e9
                 entry["frac_hbm"] = entry["achieved_gbs"] / peak
+            if name in alg_flops:
+                entry["alg_tflops"] = alg_flops[name] / (avg_ms * 1e-3) / 1e12
+                entry["frac_tensor_bf16_peak"] = entry["alg_tflops"] / tensor_peak
             kernels[name] = entry
+    # the kernel with the largest share of the step; every kernel of this path has HBM as its higher floor
     dominant = max((k for k in kernels if k in alg_bytes), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
     roofline = {
-        "kernel": {"message": "edge_message_kernel", "reduce": "segment_reduce_kernel", "gru": "gru_update_kernel"}[dominant],
-        "bound": "hbm", "achieved": kernels[dominant]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-        "frac": kernels[dominant]["frac_hbm"], "traffic": None, "peak_source": peak_src,
-        "note": "fp32 FFMA path: the two GEMM-bearing kernels are FP32-compute-bound, the segmented reduce is the HBM-bound one",
+        "kernel": kernels[dominant]["kernel"], "bound": "hbm", "achieved": kernels[dominant]["achieved_gbs"], "peak": peak,
+        "unit": "GB/s", "frac": kernels[dominant]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dominant), "peak_source": peak_src,
+        "note": "dominant kernel by time; its HBM floor exceeds its bf16-tensor floor, but it runs fp32-exact 3xTF32 MMAs "
+                "(3 tensor instructions per K=8 step), see kernels[*].alg_tflops; the HBM-bound kernel proper is "
+                "segment_reduce_stream_kernel (kernels.reduce.frac_hbm)",
     }
     b_min = 2 * n_nodes * HIDDEN * 4 + 8 * E + (T * D * HIDDEN + 6 * HIDDEN * HIDDEN + 6 * HIDDEN) * 4
     layer_ms = ms_step / NUM_LAYERS
