@@ -98,3 +98,38 @@ def test_layer_is_deterministic_and_does_not_modify_input():
         a = layer(hc, adj_c)
         b = layer(hc, adj_c)
     assert torch.equal(a, b) and torch.equal(hc.cpu(), h) and a.data_ptr() != hc.data_ptr()
+
+
+def test_layers_with_no_edges_at_all():
+    """Every edge type empty: aggregation is all zeros (torch_scatter: empty -> 0), the node update still runs."""
+    import ptgnn_b200 as P
+
+    torch.manual_seed(3)
+    n, H = 300, 64
+    h = torch.randn(n, H, generator=torch.Generator().manual_seed(1))
+    adj = [(torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)) for _ in range(2)]
+    gated = P.GatedMessagePassingLayer(H, H, 2, "max")
+    ref = O.gated_layer_forward(h, adj, [torch.empty(0, 0)] * 2, aggregation_fn="max",
+                                **gated_oracle_args({k: v.clone() for k, v in gated.state_dict().items()}))
+    assert_close(_run(gated, h, adj), ref, what="gated, E = 0")
+    mlp = P.MlpMessagePassingLayer(H, H, H, 2, "sum")
+    sd = {k: v.clone() for k, v in mlp.state_dict().items()}
+    p = "_MlpMessagePassingLayer__"
+    ref = O.mlp_layer_forward(h, adj, [torch.empty(0, 0)] * 2,
+                              [[sd[f"{p}edge_message_transformation_layers.{t}._MLP__mlp_modules.1.weight"]] for t in range(2)], "sum",
+                              ln_weight=sd[p + "state_update.0.weight"], ln_bias=sd[p + "state_update.0.bias"],
+                              dense_weight=sd[p + "state_update.1.weight"], dense_bias=sd[p + "state_update.1.bias"])
+    assert_close(_run(mlp, h, adj), ref, what="mlp, E = 0")
+
+
+def test_single_node_and_single_edge():
+    import ptgnn_b200 as P
+
+    torch.manual_seed(4)
+    H = 32
+    h = torch.randn(1, H)
+    adj = [(torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64))]
+    layer = P.GatedMessagePassingLayer(H, H, 1, "sum")
+    ref = O.gated_layer_forward(h, adj, [torch.empty(1, 0)], aggregation_fn="sum",
+                                **gated_oracle_args({k: v.clone() for k, v in layer.state_dict().items()}))
+    assert_close(_run(layer, h, adj), ref, what="N = 1")
