@@ -379,11 +379,13 @@ def main():
         launches0 = N.launch_count()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        t_host = time.perf_counter()
         for _ in range(steps):
             fn()
         if finish:
             finish()
         b.record()
+        timed.host_ms = (time.perf_counter() - t_host) * 1e3 / steps   # host enqueue time per step (no device sync)
         barrier()
         ms = a.elapsed_time(b)
         t = torch.tensor([ms], device=dev)
@@ -402,6 +404,7 @@ def main():
     ms_e2e_serial, _ = timed(step_e2e, args.steps, args.warmup)
     pipe = PipelinedE2E()
     ms_e2e, _ = timed(pipe.step, args.steps, args.warmup, finish=pipe.finish)
+    host_ms_e2e = timed.host_ms
 
     total_edges = E * world
     value = total_edges * NUM_LAYERS / (ms_step * 1e-3)
@@ -475,7 +478,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": "pipelined over steps on 3 streams: H2D(i+1) and D2H(i-1) overlap the kernels of step i; every step copies "
                             "its inputs from pinned host memory and its result back",
-                    "serial_value": total_edges * NUM_LAYERS / (ms_e2e_serial * 1e-3), "serial_ms_per_step": ms_e2e_serial},
+                    "serial_value": total_edges * NUM_LAYERS / (ms_e2e_serial * 1e-3), "serial_ms_per_step": ms_e2e_serial,
+                    "host_enqueue_ms_per_step": host_ms_e2e},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
             "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "cpu_baseline": cpu,
         }

@@ -52,20 +52,6 @@ struct TimedScope {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// Bump allocator over a caller-provided workspace (256-byte aligned slices).
-struct Workspace {
-    char *base;
-    size_t size, used;
-    Workspace(void *p, size_t n) : base(static_cast<char *>(p)), size(n), used(0) {}
-    template <typename T>
-    T *take(size_t count) {
-        size_t bytes = align_up(count * sizeof(T), 256);
-        if (used + bytes > size) return nullptr;
-        T *r = reinterpret_cast<T *>(base + used);
-        used += bytes;
-        return r;
-    }
-};
 static inline size_t ws_slice(size_t count, size_t elt) { return align_up(count * elt, 256); }
 
 // ---- per-type edge tables passed by value as a kernel parameter (< 4 KB) -------------------------
@@ -104,23 +90,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---- L2 residency control ---------------------------------------------------------------------------------------
-// The per-layer working set (messages 566 MB written + read once) streams through a 126 MB L2 that would otherwise
-// keep the 105 MB of node states every gather hits: messages are tagged evict-first, gathered state rows evict-last.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+// Optional (PTGNN_L2_HINTS=4): read the message rows in the reduce with an evict-first L2 policy.  Measured on B200:
+// no gain (and `cp.async ... L2::cache_hint` for the gathers faults), so the default is plain streaming loads.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
-}
-__device__ __forceinline__ void cp_async16_hint(uint32_t dst_smem, const void *src, uint64_t policy) {   // full 16 bytes
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "l"(policy));
-}
-__device__ __forceinline__ void st_f4_hint(float *p, const float4 &v, uint64_t policy) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
 }
 __device__ __forceinline__ float4 ld_stream_f4_hint(const float4 *p, uint64_t policy) {
     float4 r;

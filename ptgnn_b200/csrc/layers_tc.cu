@@ -100,7 +100,6 @@ struct MsgPolicy {
         float *msg;
         int H, D, Kw, use_target, num_types, n_blocks, dbg;
         unsigned long long *trace;
-        int hints;   // L2 residency hints: 1 = gathers evict-last, 2 = message stores evict-first
         int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
         int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
     };
@@ -167,7 +166,6 @@ struct GruPolicy {
         float *out;
         int num_nodes, H, D, n_jb, dbg;
         unsigned long long *trace;
-        int hints;   // L2 residency hints: 1 = gathers evict-last, 2 = message stores evict-first
     };
     struct Tile { int row0, jb; };
 
@@ -233,7 +231,6 @@ struct DensePolicy {
         float *out;
         int num_nodes, D, Hout, act, n_blocks, dbg;
         unsigned long long *trace;
-        int hints;   // L2 residency hints: 1 = gathers evict-last, 2 = message stores evict-first
     };
     struct Tile { int row0, n0, b_rows; };
 
@@ -348,7 +345,6 @@ static int launch_pipeline(typename Policy::Params &p, int total_tiles, int cate
     if (total_tiles <= 0) return PTGNN_OK;
     p.dbg = debug_flags();
     p.trace = trace_buffer(category);
-    p.hints = l2_hint_flags();
     const bool ts = mode_override() < 0 ? ts_default : mode_override() == 1;
     return ts ? launch_mode<Policy, true>(p, total_tiles, category, st) : launch_mode<Policy, false>(p, total_tiles, category, st);
 }

@@ -114,9 +114,8 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, i
 // different 128-byte lines.  Staging 32 rows x NCOLS through a (chunk-XOR-swizzled) buffer lets each store
 // instruction write whole rows: 4 (NCOLS = 32) or 8 (NCOLS = 16) lines per instruction instead of 32.
 // `row_off` is this lane's destination element offset from `dst_base` (negative = row not stored).
-template <int NCOLS, bool STREAM = false>
-__device__ __forceinline__ void warp_store_rows(float *stage, const float *v, float *dst_base, long long row_off, int lane,
-                                                uint64_t policy = 0) {
+template <int NCOLS>
+__device__ __forceinline__ void warp_store_rows(float *stage, const float *v, float *dst_base, long long row_off, int lane) {
     constexpr int CPR = NCOLS / 4;   // 16-byte chunks per row
 #pragma unroll
     for (int j = 0; j < CPR; ++j)
@@ -128,10 +127,7 @@ __device__ __forceinline__ void warp_store_rows(float *stage, const float *v, fl
         const int idx = it * 32 + lane, row = idx / CPR, ch = idx % CPR;
         const float4 val = *reinterpret_cast<const float4 *>(stage + (row * CPR + (ch ^ (row & (CPR - 1)))) * 4);
         const long long off = __shfl_sync(0xffffffffu, row_off, row);
-        if (off >= 0) {
-            if (STREAM) st_f4_hint(dst_base + off + ch * 4, val, policy);   // written once, read once: L2 evict-first
-            else *reinterpret_cast<float4 *>(dst_base + off + ch * 4) = val;
-        }
+        if (off >= 0) *reinterpret_cast<float4 *>(dst_base + off + ch * 4) = val;
     }
     __syncwarp();
 }
