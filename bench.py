@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agg", default="sum", choices=["sum", "max", "mean", "min"])
     ap.add_argument("--workload", default="graph2class", choices=["graph2class", "varmisuse"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="node-state dtype; f32 is the headline (reference CPU path precision), bf16 = BASELINE.json configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="only the HBM-resident loop (for runs under ncu); prints no bench line")
     args = ap.parse_args()
@@ -237,10 +239,10 @@ def main():
     metric = "edges/sec per GNN layer"
     config = {
         "workload": f"{args.workload} synthetic batch per GPU: 80x2560=204,800 nodes, 8 raw edge types -> T=17, E=1,105,920 "
-                    f"layer-level edges, hidden {HIDDEN}, {NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), fp32"
+                    f"layer-level edges, hidden {HIDDEN}, {NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), {args.dtype}"
                     if args.workload == "graph2class" else
                     f"varmisuse synthetic batch per GPU: 40x2000 nodes, 11 raw types -> T=23, E=480,000, hidden {HIDDEN}, "
-                    f"{NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), fp32",
+                    f"{NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), {args.dtype}",
         "step": "edge-plan build + 8 layers on one minibatch",
         "parallelism": f"graph-sharded x{world} (no data-path collective)",
         "l2": "per-layer working set ~0.8 GB (messages 566 MB + states) > 126 MB L2; no explicit flush",
@@ -283,9 +285,11 @@ def main():
     n_nodes = batch.num_nodes
 
     gen = torch.Generator().manual_seed(7 + rank)
-    h_host = torch.randn(n_nodes, HIDDEN, generator=gen).pin_memory()
+    state_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    esz = 2 if args.dtype == "bf16" else 4
+    h_host = torch.randn(n_nodes, HIDDEN, generator=gen).to(state_dtype).pin_memory()
     adj_host = [(s.pin_memory(), t.pin_memory()) for s, t in batch.adjacency_lists]
-    out_host = torch.empty(n_nodes, HIDDEN).pin_memory()
+    out_host = torch.empty(n_nodes, HIDDEN, dtype=state_dtype).pin_memory()
     h_dev = h_host.to(dev)
     adj_dev = [(s.to(dev), t.to(dev)) for s, t in adj_host]
     n2g = batch.node_to_graph_idx.to(dev)
@@ -319,7 +323,7 @@ def main():
             self.h2d, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.h_buf = [torch.empty_like(h_dev) for _ in range(2)]
             self.adj_buf = [[(torch.empty_like(s), torch.empty_like(t)) for s, t in adj_dev] for _ in range(2)]
-            self.out_host = [torch.empty(n_nodes, HIDDEN).pin_memory() for _ in range(2)]
+            self.out_host = [torch.empty(n_nodes, HIDDEN, dtype=state_dtype).pin_memory() for _ in range(2)]
             self.in_ready = [torch.cuda.Event() for _ in range(2)]
             self.compute_done = [torch.cuda.Event() for _ in range(2)]
             self.d2h_done = [torch.cuda.Event() for _ in range(2)]
@@ -409,8 +413,8 @@ def main():
     total_edges = E * world
     value = total_edges * NUM_LAYERS / (ms_step * 1e-3)
     e2e_value = total_edges * NUM_LAYERS / (ms_e2e * 1e-3)
-    h2d = h_host.numel() * 4 + sum(s.numel() * 8 + t.numel() * 8 for s, t in adj_host)
-    d2h = out_host.numel() * 4
+    h2d = h_host.numel() * esz + sum(s.numel() * 8 + t.numel() * 8 for s, t in adj_host)
+    d2h = out_host.numel() * esz
 
     # ---- per-kernel timing leg (CUDA events on the launch stream, inside the library) -> roofline
     N.kernel_timing(True)
@@ -425,10 +429,10 @@ def main():
     peak, peak_src = measured_peaks()
     tensor_peak = measured_tensor_peak()
     D = HIDDEN
-    alg_bytes = {  # per launch, see DESIGN.md section 3 ("alg. bytes")
-        "message": n_nodes * HIDDEN * 4 + E * (D * 4 + 8),
-        "reduce": E * D * 4 + (n_nodes + 1) * 4 + n_nodes * D * 4,
-        "gru": n_nodes * D * 4 + 2 * n_nodes * HIDDEN * 4 + 6 * HIDDEN * HIDDEN * 4,
+    alg_bytes = {  # per launch, see DESIGN.md section 3 ("alg. bytes"); esz = bytes per state / message element
+        "message": n_nodes * HIDDEN * esz + E * (D * esz + 8),
+        "reduce": E * D * esz + (n_nodes + 1) * 4 + n_nodes * D * esz,
+        "gru": n_nodes * D * esz + 2 * n_nodes * HIDDEN * esz + 6 * HIDDEN * HIDDEN * esz,
     }
     alg_flops = {  # fp32 multiply-adds the reference performs (x2); the 3xTF32 path issues 3x this on the tensor cores
         "message": 2 * E * HIDDEN * D,
@@ -436,6 +440,9 @@ def main():
     }
     kernel_names = {"message": "tc_pipeline_kernel<MsgPolicy> (edge messages)", "reduce": "segment_reduce_stream_kernel",
                     "gru": "tc_pipeline_kernel<GruPolicy> (GRUCell update)", "plan": "edge-plan kernels", "pack": "weight split/pack"}
+    if args.dtype == "bf16":
+        kernel_names.update(message="tc_pipeline_bf16_kernel<MsgPolicyB>", reduce="segment_reduce_bf16_kernel",
+                            gru="tc_pipeline_bf16_kernel<GruPolicyB>")
     kernels = {}
     for name, (ms, cnt) in kt.items():
         if cnt:
@@ -454,26 +461,27 @@ def main():
     dominant = max((k for k in kernels if k in alg_bytes), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
     roofline = {
         "kernel": kernels[dominant]["kernel"], "bound": "hbm", "achieved": kernels[dominant]["achieved_gbs"], "peak": peak,
-        "unit": "GB/s", "frac": kernels[dominant]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dominant), "peak_source": peak_src,
+        "unit": "GB/s", "frac": kernels[dominant]["frac_hbm"],
+        "traffic": NCU_TRAFFIC.get(dominant) if args.dtype == "f32" else None, "peak_source": peak_src,
         "note": "dominant kernel by time; its HBM floor exceeds its bf16-tensor floor, but it runs fp32-exact 3xTF32 MMAs "
                 "(3 tensor instructions per K=8 step), see kernels[*].alg_tflops; the HBM-bound kernel proper is "
                 "segment_reduce_stream_kernel (kernels.reduce.frac_hbm)",
     }
-    b_min = 2 * n_nodes * HIDDEN * 4 + 8 * E + (T * D * HIDDEN + 6 * HIDDEN * HIDDEN + 6 * HIDDEN) * 4
+    b_min = 2 * n_nodes * HIDDEN * esz + 8 * E + (T * D * HIDDEN + 6 * HIDDEN * HIDDEN + 6 * HIDDEN) * esz
     layer_ms = ms_step / NUM_LAYERS
     layer_roofline = {"alg_bytes_fully_fused": b_min, "achieved_gbs": b_min / (layer_ms * 1e-3) / 1e9,
                       "frac": b_min / (layer_ms * 1e-3) / 1e9 / peak, "ms_per_layer": layer_ms,
                       "nodes_per_sec_per_layer": n_nodes * world / (layer_ms * 1e-3)}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.dtype == "f32":
         r = cpu_reference_run(batch, gnn, args.agg, steps=3, warmup=1, budget_s=25.0)
         cpu = {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": config, "clocks": clock_summary,
             "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": "pipelined over steps on 3 streams: H2D(i+1) and D2H(i-1) overlap the kernels of step i; every step copies "

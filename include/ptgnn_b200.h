@@ -128,6 +128,19 @@ int ptgnn_b200_gated_forward_f32(const float *node_states, const float *gather_s
                                  const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh, int32_t reduce,
                                  float *out_states, void *workspace, size_t workspace_bytes, void *stream);
 
+/* bf16 variant (BASELINE.json configs[3]): node_states / gather_states / out_states are bf16 [*, H] (raw uint16 bits),
+ * module parameters stay fp32 and are converted per call; messages and aggregates are bf16 in HBM, every accumulation
+ * (tensor-core accumulators, segmented reduce, gate math) is fp32 -- the arithmetic of the reference under
+ * torch.autocast(bfloat16) (fp32 scatter: abstractmessagepassing.py:43-50).  Needs H % 32 == 0, D % 16 == 0, 64 <= D <= 256. */
+size_t ptgnn_b200_gated_workspace_bytes_bf16(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t state_dim,
+                                             int32_t message_dim);
+int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const uint16_t *gather_states /* NULL: node_states */,
+                                  int64_t num_nodes, int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                  const int64_t *type_off /*[host]*/, const int32_t *row_ptr, const int32_t *pos,
+                                  const int32_t *src32, const float *const *edge_weights /*[host] T device pointers, fp32*/,
+                                  const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                                  int32_t reduce, uint16_t *out_states, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * MlpMessagePassingLayer.forward (mlpmessagepassing.py:68-117), eval mode, default message MLP
  * (mlp_hidden_layers = 0: one bias-free Linear, mlp.py:65-74), string aggregator, no edge features:

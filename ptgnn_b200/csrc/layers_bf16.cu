@@ -1,0 +1,424 @@
+// bf16 GatedMessagePassingLayer forward (BASELINE.json configs[3]: bf16 states): bf16 node states / messages / weights,
+// fp32 accumulation everywhere (tensor-core accumulators, segmented reduce, gate math) -- the arithmetic of the
+// reference under torch.autocast(bfloat16), whose scatter is always fp32 (abstractmessagepassing.py:43-50).
+//   reference ptgnn/neuralmodels/gnn/messagepassing/gatedmessagepassing.py:37-69
+// Kernels: weight conversion/packing -> tc_pipeline_bf16_kernel<MsgPolicyB> -> segment_reduce_bf16_kernel ->
+// tc_pipeline_bf16_kernel<GruPolicyB>.
+#include <float.h>
+#include <stdlib.h>
+
+#include "tc_pipeline_bf16.cuh"
+
+namespace ptgnn {
+namespace tcb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+// bf16 row-major [rows, cols], box = {64 columns (128 bytes), box_rows}, SWIZZLE_128B, OOB zero fill
+static int make_map_bf16(CUtensorMap *map, const __nv_bfloat16 *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return PTGNN_E_CUDA; }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {(cuuint32_t)CHUNK_K, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(base), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r); return PTGNN_E_CUDA; }
+    return PTGNN_OK;
+}
+
+// ---- weights: fp32 module parameters -> bf16 working copies ---------------------------------------------------
+struct ConvSrc {
+    const float *w[PTGNN_MAX_EDGE_TYPES];
+    int num, elems;
+};
+__global__ void convert_weights_kernel(const __grid_constant__ ConvSrc s, __nv_bfloat16 *__restrict__ out) {
+    const int64_t total = (int64_t)s.num * s.elems;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(s.w[i / s.elems][i % s.elems]);
+}
+// same gate-blocked layout as the fp32 path: P1[jb] = [W_ir; W_iz; W_in; 0], P2[jb] = [W_hr; W_hz; 0; W_hn] (128 rows each)
+__global__ void pack_gru_bf16_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh, int H, int D,
+                                     __nv_bfloat16 *__restrict__ p1, __nv_bfloat16 *__restrict__ p2) {
+    const int nblk = H / 32;
+    const int64_t n1 = (int64_t)nblk * 128 * D, n2 = (int64_t)nblk * 128 * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int k = (int)(i % D), n = (int)((i / D) % 128), jb = (int)(i / ((int64_t)128 * D));
+            const int gate = n / 32;
+            p1[i] = __float2bfloat16_rn(gate < 3 ? w_ih[(size_t)(gate * H + jb * 32 + n % 32) * D + k] : 0.0f);
+        } else {
+            const int64_t r = i - n1;
+            const int k = (int)(r % H), n = (int)((r / H) % 128), jb = (int)(r / ((int64_t)128 * H));
+            const int gate = n / 32;
+            p2[r] = __float2bfloat16_rn(gate == 2 ? 0.0f : w_hh[(size_t)((gate == 3 ? 2 : gate) * H + jb * 32 + n % 32) * H + k]);
+        }
+    }
+}
+
+// ---- policy: per-edge messages -------------------------------------------------------------------------------
+struct MsgPolicyB {
+    struct Params {
+        CUtensorMap map_w;                 // [T*D, H] bf16, box {64, min(128, D)}
+        const __nv_bfloat16 *h;            // rows indexed by src32
+        const int32_t *src32, *pos;
+        __nv_bfloat16 *msg;                // [E, D] bf16 at target-sorted rows
+        int H, D, num_types, n_blocks;
+        int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
+        int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
+    };
+    struct Tile { int t, e0, e_end, n0, b_rows; };
+    __device__ static int num_tiles(const Params &p) { return p.tile_off[p.num_types] * p.n_blocks; }
+    __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
+        const int mt = tile / p.n_blocks, nb = tile % p.n_blocks;
+        int lo = 0, hi = p.num_types - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.tile_off[mid] <= mt) lo = mid; else hi = mid - 1;
+        }
+        ti.t = lo;
+        ti.e0 = p.edge_off[lo] + (mt - p.tile_off[lo]) * TILE_M;
+        ti.e_end = p.edge_off[lo + 1];
+        ti.n0 = nb * 128;
+        ti.b_rows = min(128, p.D - ti.n0);
+    }
+    __device__ static int num_segments(const Params &, const Tile &) { return 1; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int) {
+        Segment s;
+        s.a = p.h; s.lda = p.H; s.K = p.H; s.a_map = nullptr; s.a_row0 = 0;
+        s.b_map = &p.map_w; s.b_row0 = ti.t * p.D + ti.n0; s.b_col0 = 0; s.b_box_rows = min(128, p.D);
+        return s;
+    }
+    __device__ static int gather_row(const Params &p, const Tile &ti, int, int r) {
+        const int e = ti.e0 + r;
+        return e < ti.e_end ? p.src32[e] : -1;
+    }
+    __device__ static int mma_groups(const Params &, const Tile &ti, int, MmaGroup (&g)[2]) {
+        g[0] = MmaGroup{ti.b_rows, 0, 0, true};
+        return 1;
+    }
+    __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
+        drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
+    }
+    // offsets are in 4-byte words of the bf16 message array (2 bf16 per word)
+    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+        const int e = ti.e0 + quarter * 32 + lane;
+        return e < ti.e_end ? ((long long)p.pos[e] * p.D + ti.n0) / 2 : -1;
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off, int half, int lane, float *stage) {
+        const int c0 = 64 * half;            // this warp's 64 accumulator columns -> 32 packed words
+        if (c0 >= ti.b_rows) return;
+        float w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
+        float *dst = reinterpret_cast<float *>(p.msg) + c0 / 2;
+        if (ti.b_rows - c0 >= 64) tc::warp_store_rows<32>(stage, w, dst, row_off, lane);
+        else if (ti.b_rows - c0 >= 32) tc::warp_store_rows<16>(stage, w, dst, row_off, lane);
+        else tc::warp_store_rows<8>(stage, w, dst, row_off, lane);   // 16 columns
+    }
+};
+
+// ---- policy: GRUCell ---------------------------------------------------------------------------------------------
+struct GruPolicyB {
+    struct Params {
+        CUtensorMap map_agg, map_h, map_p1, map_p2;
+        const __nv_bfloat16 *h;
+        const float *b_ih, *b_hh;
+        __nv_bfloat16 *out;
+        int num_nodes, H, D, n_jb;
+    };
+    struct Tile { int row0, jb; };
+    __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_jb; }
+    __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
+        ti.row0 = (tile / p.n_jb) * TILE_M;
+        ti.jb = tile % p.n_jb;
+    }
+    __device__ static int num_segments(const Params &, const Tile &) { return 2; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
+        Segment s;
+        s.a = nullptr; s.lda = 0; s.a_row0 = ti.row0; s.b_row0 = ti.jb * 128; s.b_col0 = 0; s.b_box_rows = 128;
+        if (seg == 0) { s.a_map = &p.map_agg; s.K = p.D; s.b_map = &p.map_p1; }
+        else { s.a_map = &p.map_h; s.K = p.H; s.b_map = &p.map_p2; }
+        return s;
+    }
+    __device__ static int gather_row(const Params &, const Tile &, int, int) { return -1; }
+    __device__ static int mma_groups(const Params &, const Tile &, int seg, MmaGroup (&g)[2]) {
+        g[0] = MmaGroup{128, 0, 0, seg == 0};
+        return 1;
+    }
+    __device__ static void drain(const Params &, const Tile &, uint32_t tmem_lane, int half, float (&acc)[64]) {
+        drain_4x16(tmem_lane, 16 * half, acc);
+    }
+    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+        const int row = ti.row0 + quarter * 32 + lane;
+        return row < p.num_nodes ? ((long long)row * p.H + ti.jb * 32) / 2 : -1;   // 4-byte words
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off0, int half, int lane, float *stage) {
+        const int H = p.H;
+        const int j0 = ti.jb * 32 + 16 * half;
+        const long long row_off = row_off0 < 0 ? -1 : row_off0 + 8 * half;
+        float hw[8];                                                               // 16 bf16 = 8 words of h[row][j0 .. j0+16)
+        tc::warp_load_rows<8>(stage, hw, reinterpret_cast<const float *>(p.h), row_off, lane);
+        float ow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 hp = *reinterpret_cast<const __nv_bfloat162 *>(&hw[i]);
+            const float hv[2] = {__low2float(hp), __high2float(hp)};
+            float o[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int ii = 2 * i + u, j = j0 + ii;
+                const float rr = sigmoid_f(acc[ii] + (p.b_ih[j] + p.b_hh[j]));
+                const float zz = sigmoid_f(acc[16 + ii] + (p.b_ih[H + j] + p.b_hh[H + j]));
+                const float nn = tanhf(acc[32 + ii] + p.b_ih[2 * H + j] + rr * (acc[48 + ii] + p.b_hh[2 * H + j]));
+                o[u] = (1.0f - zz) * nn + zz * hv[u];
+            }
+            ow[i] = pack_bf16x2(o[0], o[1]);
+        }
+        tc::warp_store_rows<8>(stage, ow, reinterpret_cast<float *>(p.out), row_off, lane);
+    }
+};
+
+// ---- segmented reduce over bf16 message rows (fp32 accumulation, bf16 result) ------------------------------------
+// Same flat streaming walk as segment_reduce_stream_kernel (reduce.cuh); a lane owns 4 consecutive bf16 columns
+// (8-byte loads), CHUNKS x 128 columns per row.
+template <int RED, int CHUNKS>
+__global__ void __launch_bounds__(256)
+segment_reduce_bf16_kernel(const __nv_bfloat16 *__restrict__ msg, const int32_t *__restrict__ row_ptr, int num_nodes, int D,
+                           __nv_bfloat16 *__restrict__ out) {
+    constexpr int ROWS_PER_WARP = 16;
+    constexpr int UNROLL = CHUNKS == 1 ? 8 : 4;
+    const int lane = threadIdx.x & 31;
+    const int r0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS_PER_WARP;
+    if (r0 >= num_nodes) return;
+    const int nrows = min(ROWS_PER_WARP, num_nodes - r0);
+    const int bound = row_ptr[r0 + min(lane, nrows)];
+    const int j_begin = __shfl_sync(0xffffffffu, bound, 0), j_end = __shfl_sync(0xffffffffu, bound, nrows);
+    bool col_ok[CHUNKS];
+    float4 acc[CHUNKS];
+    const float init = RED == PTGNN_REDUCE_MAX ? -FLT_MAX : (RED == PTGNN_REDUCE_MIN ? FLT_MAX : 0.0f);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) { col_ok[c] = (c * 32 + lane) * 4 < D; acc[c] = make_float4(init, init, init, init); }
+    const size_t ld2 = (size_t)D / 4;   // row pitch in uint2 (4 bf16)
+    const uint2 *msg2 = reinterpret_cast<const uint2 *>(msg);
+    uint2 *out2 = reinterpret_cast<uint2 *>(out);
+    int cur = 0, cur_end = __shfl_sync(0xffffffffu, bound, 1);
+
+    auto flush = [&](int row, int count) {
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            float4 a = acc[c];
+            if (RED == PTGNN_REDUCE_MEAN) { const float n = (float)(count < 1 ? 1 : count); a.x /= n; a.y /= n; a.z /= n; a.w /= n; }
+            if (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN) {
+                if (a.x == init) a.x = 0.f; if (a.y == init) a.y = 0.f; if (a.z == init) a.z = 0.f; if (a.w == init) a.w = 0.f;
+            }
+            if (col_ok[c]) {
+                uint2 o;
+                o.x = __float_as_uint(pack_bf16x2(a.x, a.y));
+                o.y = __float_as_uint(pack_bf16x2(a.z, a.w));
+                out2[(size_t)(r0 + row) * ld2 + c * 32 + lane] = o;
+            }
+            acc[c] = make_float4(init, init, init, init);
+        }
+    };
+    auto comb = [&](float &a, float m) {
+        if (RED == PTGNN_REDUCE_MAX) { if (m > a) a = m; }
+        else if (RED == PTGNN_REDUCE_MIN) { if (m < a) a = m; }
+        else a += m;
+    };
+    for (int j = j_begin; j < j_end; j += UNROLL) {
+        uint2 m[UNROLL][CHUNKS];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (j + u < j_end) {
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c)
+                    if (col_ok[c]) m[u][c] = __ldg(msg2 + (size_t)(j + u) * ld2 + c * 32 + lane);
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int jj = j + u;
+            if (jj < j_end) {
+                while (jj >= cur_end) {
+                    const int beg = __shfl_sync(0xffffffffu, bound, cur);
+                    flush(cur, cur_end - beg);
+                    ++cur;
+                    cur_end = __shfl_sync(0xffffffffu, bound, cur + 1);
+                }
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c)
+                    if (col_ok[c]) {
+                        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162 *>(&m[u][c].x);
+                        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162 *>(&m[u][c].y);
+                        comb(acc[c].x, __low2float(lo)); comb(acc[c].y, __high2float(lo));
+                        comb(acc[c].z, __low2float(hi)); comb(acc[c].w, __high2float(hi));
+                    }
+            }
+        }
+    }
+    for (; cur < nrows; ++cur) {
+        const int beg = __shfl_sync(0xffffffffu, bound, cur), end = __shfl_sync(0xffffffffu, bound, cur + 1);
+        flush(cur, end - beg);
+    }
+}
+
+template <int RED>
+static int launch_reduce_bf16(const __nv_bfloat16 *msg, const int32_t *row_ptr, int64_t N, int D, __nv_bfloat16 *out, cudaStream_t st) {
+    const unsigned grid = (unsigned)ceil_div(N, 8 * 16);
+    {
+        TimedScope timed__(PTGNN_KERNEL_REDUCE, st);
+        if (D <= 128) segment_reduce_bf16_kernel<RED, 1><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out);
+        else segment_reduce_bf16_kernel<RED, 2><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+template <class Policy>
+static int launch_pipeline(const typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
+    if (total_tiles <= 0) return PTGNN_OK;
+    static bool configured = false;
+    if (!configured) {
+        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_bf16_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    {
+        TimedScope timed__(category, st);
+        tc_pipeline_bf16_kernel<Policy><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+struct WsB { size_t msg, agg, w, p1, p2, total; };
+static WsB ws_layout(int64_t N, int64_t E, int T, int H, int D) {
+    WsB w{};
+    size_t o = 0;
+    auto add = [&](size_t cnt) { size_t at = o; o += ws_slice(cnt, 2); return at; };
+    w.msg = add((size_t)E * D + 8);
+    w.agg = add((size_t)N * D + 8);
+    w.w = add((size_t)T * D * H + 8);
+    w.p1 = add((size_t)(H / 32 + 1) * 128 * D);
+    w.p2 = add((size_t)(H / 32 + 1) * 128 * H);
+    w.total = o;
+    return w;
+}
+
+}  // namespace tcb
+}  // namespace ptgnn
+
+using namespace ptgnn;
+using namespace ptgnn::tcb;
+
+extern "C" size_t ptgnn_b200_gated_workspace_bytes_bf16(int64_t num_nodes, int64_t num_edges, int32_t num_types,
+                                                        int32_t state_dim, int32_t message_dim) {
+    if (num_nodes < 0 || num_edges < 0 || num_types < 0 || state_dim <= 0 || message_dim <= 0) return 0;
+    return ws_layout(num_nodes, num_edges, num_types, state_dim, message_dim).total;
+}
+
+extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const uint16_t *gather_states, int64_t num_nodes,
+                                             int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                             const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
+                                             const int32_t *src32, const float *const *edge_weights, const float *gru_w_ih,
+                                             const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                                             int32_t reduce, uint16_t *out_states, void *workspace, size_t workspace_bytes,
+                                             void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int H = state_dim, D = message_dim;
+    PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && type_off, "gated_forward_bf16: bad num_types=%d", num_types);
+    const int64_t E = type_off[num_types];
+    PTGNN_CHECK_ARG(num_nodes >= 0 && num_nodes < INT32_MAX && E >= 0 && E < INT32_MAX, "gated_forward_bf16: sizes out of range");
+    if (H % 32 != 0 || D % 16 != 0 || H < 64 || D < 64 || D > 256 || H > 1024) {
+        set_error("gated_forward_bf16: needs state dim %% 32 == 0 (>= 64) and message dim %% 16 == 0 in [64, 256]; got %d, %d", H, D);
+        return PTGNN_E_UNSUPPORTED;
+    }
+    PTGNN_CHECK_ARG(reduce >= PTGNN_REDUCE_SUM && reduce <= PTGNN_REDUCE_MIN, "gated_forward_bf16: bad reduce %d", reduce);
+    if (num_nodes == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(node_states && out_states && row_ptr && gru_w_ih && gru_w_hh && gru_b_ih && gru_b_hh, "gated_forward_bf16: null pointer");
+    PTGNN_CHECK_ARG(E == 0 || (pos && src32 && edge_weights), "gated_forward_bf16: null edge arrays");
+    const WsB L = ws_layout(num_nodes, E, num_types, H, D);
+    if (workspace_bytes < L.total || !workspace) {
+        set_error("gated_forward_bf16: workspace %zu < required %zu", workspace_bytes, L.total);
+        return PTGNN_E_WORKSPACE;
+    }
+    char *ws = static_cast<char *>(workspace);
+    auto b16 = [&](size_t off) { return reinterpret_cast<__nv_bfloat16 *>(ws + off); };
+    const __nv_bfloat16 *h = reinterpret_cast<const __nv_bfloat16 *>(node_states);
+    const __nv_bfloat16 *hsrc = gather_states ? reinterpret_cast<const __nv_bfloat16 *>(gather_states) : h;
+    __nv_bfloat16 *msg = b16(L.msg), *agg = b16(L.agg), *wb = b16(L.w), *p1 = b16(L.p1), *p2 = b16(L.p2);
+
+    // 0. weights -> bf16 (edge weights [T][D][H]; GRU gate blocks)
+    ConvSrc cs{};
+    cs.num = num_types; cs.elems = D * H;
+    for (int t = 0; t < num_types; ++t) cs.w[t] = edge_weights[t];
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        convert_weights_kernel<<<148, 256, 0, st>>>(cs, wb);
+    }
+    PTGNN_LAUNCHED();
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_gru_bf16_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, p1, p2);
+    }
+    PTGNN_LAUNCHED();
+
+    // 1. messages
+    MsgPolicyB::Params mp{};
+    int rc = make_map_bf16(&mp.map_w, wb, (uint64_t)num_types * D, H, D < 128 ? D : 128);
+    if (rc) return rc;
+    mp.h = hsrc; mp.src32 = src32; mp.pos = pos; mp.msg = msg; mp.H = H; mp.D = D; mp.num_types = num_types;
+    mp.n_blocks = (D + 127) / 128;
+    int tiles = 0;
+    for (int t = 0; t < num_types; ++t) {
+        mp.edge_off[t] = (int32_t)type_off[t];
+        mp.tile_off[t] = tiles;
+        tiles += (int)ceil_div(type_off[t + 1] - type_off[t], TILE_M);
+    }
+    for (int t = num_types; t <= PTGNN_MAX_EDGE_TYPES; ++t) { mp.edge_off[t] = (int32_t)type_off[num_types]; mp.tile_off[t] = tiles; }
+    rc = launch_pipeline<MsgPolicyB>(mp, tiles * mp.n_blocks, PTGNN_KERNEL_MESSAGE, st);
+    if (rc) return rc;
+
+    // 2. segmented reduce (fp32 accumulate, bf16 result)
+    switch (reduce) {
+        case PTGNN_REDUCE_SUM: rc = launch_reduce_bf16<PTGNN_REDUCE_SUM>(msg, row_ptr, num_nodes, D, agg, st); break;
+        case PTGNN_REDUCE_MEAN: rc = launch_reduce_bf16<PTGNN_REDUCE_MEAN>(msg, row_ptr, num_nodes, D, agg, st); break;
+        case PTGNN_REDUCE_MAX: rc = launch_reduce_bf16<PTGNN_REDUCE_MAX>(msg, row_ptr, num_nodes, D, agg, st); break;
+        default: rc = launch_reduce_bf16<PTGNN_REDUCE_MIN>(msg, row_ptr, num_nodes, D, agg, st); break;
+    }
+    if (rc) return rc;
+
+    // 3. GRUCell
+    GruPolicyB::Params gp{};
+    const uint64_t prow = (uint64_t)(H / 32) * 128;
+    rc = make_map_bf16(&gp.map_agg, agg, num_nodes, D, 128);
+    if (!rc) rc = make_map_bf16(&gp.map_h, h, num_nodes, H, 128);
+    if (!rc) rc = make_map_bf16(&gp.map_p1, p1, prow, D, 128);
+    if (!rc) rc = make_map_bf16(&gp.map_p2, p2, prow, H, 128);
+    if (rc) return rc;
+    gp.h = h; gp.b_ih = gru_b_ih; gp.b_hh = gru_b_hh; gp.out = reinterpret_cast<__nv_bfloat16 *>(out_states);
+    gp.num_nodes = (int)num_nodes; gp.H = H; gp.D = D; gp.n_jb = H / 32;
+    return launch_pipeline<GruPolicyB>(gp, (int)ceil_div(num_nodes, TILE_M) * gp.n_jb, PTGNN_KERNEL_GRU, st);
+}

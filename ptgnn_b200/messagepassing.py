@@ -168,10 +168,13 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         _refuse_autograd(self, node_states)
         reduce = _reduce_code(self.__aggregation_fn)
 
-        h = N.require_cuda(node_states, "node_states", torch.float32)
+        state_dtype = node_states.dtype if node_states.dtype == torch.bfloat16 else torch.float32
+        h = N.require_cuda(node_states, "node_states", state_dtype)
         num_nodes, H = h.shape
         D = self.__message_dimension
-        gsrc = self._gather_source(gather_states, h)
+        gsrc = None if gather_states is None else N.require_cuda(gather_states, "gather_states", state_dtype)
+        if gsrc is not None and (gsrc.dim() != 2 or gsrc.shape[1] != H):
+            raise ValueError("gather_states must be [num_source_nodes, H]")
         plan = self._plan(adjacency_lists, num_nodes, None if gsrc is None else gsrc.shape[0])
         gru = self.__state_update
         weights = [N.require_cuda(lin.weight, "edge weight", torch.float32) for lin in linears]
@@ -179,6 +182,18 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         b_ih, b_hh = N.require_cuda(gru.bias_ih, "bias_ih", torch.float32), N.require_cuda(gru.bias_hh, "bias_hh", torch.float32)
 
         lib = N.lib()
+        if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
+            ws_bytes = lib.ptgnn_b200_gated_workspace_bytes_bf16(num_nodes, plan.num_edges, plan.num_types, H, D)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
+            out = torch.empty_like(h)
+            with torch.cuda.device(h.device):
+                rc = lib.ptgnn_b200_gated_forward_bf16(
+                    N.ptr(h), N.ptr(gsrc), num_nodes, H, D, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
+                    N.ptr(plan.src32), N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce,
+                    N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+                )
+            N.check(rc, "ptgnn_b200_gated_forward_bf16")
+            return out
         ws_bytes = lib.ptgnn_b200_gated_workspace_bytes(num_nodes, plan.num_edges, plan.num_types, H, D)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
         out = torch.empty_like(h)

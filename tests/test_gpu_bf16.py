@@ -1,0 +1,86 @@
+"""bf16 GatedMessagePassingLayer (BASELINE.json configs[3]): bf16 states, fp32 accumulation.
+
+Two bars: (1) against an fp32 emulation of the SAME arithmetic (inputs/weights/messages/aggregates rounded to bf16 at the
+points where the kernels round) the result must agree to bf16 rounding, |d| <= 1e-2 max(1,|ref|) -- north_star's bf16
+tolerance; (2) against the plain fp32 oracle the relative L2 error must stay <= 1e-2 and 99.9 % of the elements within
+1e-2 max(1,|ref|) (the reference's own autocast path differs from its fp32 path by about that much)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import gated_oracle_args, random_adjacency
+from oracle import ptgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _emulated(h_bf16, adj, w, agg_fn):
+    """fp32 math on bf16-rounded operands, rounding where the CUDA path stores bf16 (messages, aggregate, output)."""
+    h = h_bf16.float()
+    msgs = torch.cat([_r(F.linear(F.embedding(s, h), _r(wt))) for (s, _), wt in zip(adj, w["edge_weights"])])
+    agg = _r(O.scatter(msgs, torch.cat([t for _, t in adj]), h.shape[0], agg_fn))
+    gi = F.linear(agg, _r(w["gru_w_ih"])) + w["gru_b_ih"]
+    gh = F.linear(h, _r(w["gru_w_hh"])) + w["gru_b_hh"]
+    H = h.shape[1]
+    r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+    z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+    n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+    return _r((1 - z) * n + z * h)
+
+
+@pytest.mark.parametrize("agg", ["sum", "max", "mean"])
+@pytest.mark.parametrize("n,H,counts", [(3000, 128, [9000, 7000, 0, 2000, 3000]), (1500, 64, [5000, 100]), (700, 256, [4000, 1])])
+def test_gated_bf16(agg, n, H, counts):
+    import ptgnn_b200 as P
+
+    gen = torch.Generator().manual_seed(n + H)
+    torch.manual_seed(n)
+    adj = random_adjacency(gen, n, counts)
+    h = torch.randn(n, H, generator=gen).to(torch.bfloat16)
+    layer = P.GatedMessagePassingLayer(H, H, len(counts), agg)
+    w = gated_oracle_args({k: v.clone() for k, v in layer.state_dict().items()})
+    layer = layer.cuda().eval()
+    with torch.no_grad():
+        out = layer(h.cuda(), [(s.cuda(), t.cuda()) for s, t in adj])
+    assert out.dtype == torch.bfloat16 and out.shape == h.shape
+    out = out.float().cpu()
+
+    emu = _emulated(h, adj, w, agg)
+    err = ((out - emu).abs() / emu.abs().clamp(min=1.0))
+    assert float(err.max()) <= 1e-2, f"vs bf16 emulation: max scaled error {float(err.max()):.3e}"
+    assert float(err.mean()) <= 1e-3
+
+    ref = O.gated_layer_forward(h.float(), adj, [torch.empty(c, 0) for c in counts], aggregation_fn=agg, **w)
+    rel_l2 = float((out - ref).norm() / ref.norm())
+    within = float((((out - ref).abs() / ref.abs().clamp(min=1.0)) <= 1e-2).float().mean())
+    assert rel_l2 <= 1e-2 and within >= 0.999, f"vs fp32 oracle: rel L2 {rel_l2:.3e}, within tol {within:.5f}"
+
+
+def test_bf16_rejects_unsupported_dims_loudly():
+    import ptgnn_b200 as P
+
+    layer = P.GatedMessagePassingLayer(32, 32, 1, "sum").cuda().eval()
+    adj = [(torch.zeros(3, dtype=torch.int64).cuda(), torch.zeros(3, dtype=torch.int64).cuda())]
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        layer(torch.zeros(4, 32, dtype=torch.bfloat16).cuda(), adj)
+
+
+def test_bf16_row_shards_match_unsharded():
+    import ptgnn_b200 as P
+    from ptgnn_b200 import sharding
+    from ptgnn_b200.synthetic import single_random_graph
+
+    g = single_random_graph(4001, 30000, 3, seed=3)
+    torch.manual_seed(0)
+    layer = P.GatedMessagePassingLayer(128, 128, 3, "sum").cuda().eval()
+    h = torch.randn(g.num_nodes, 128, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).cuda()
+    adj = [(s.cuda(), t.cuda()) for s, t in g.adjacency_lists]
+    with torch.no_grad():
+        ref = layer(h, adj)
+        shards = [sharding.row_shard(g.num_nodes, adj, 2, r) for r in range(2)]
+        out = torch.cat([layer(h[s.lo:s.hi].contiguous(), s.adjacency_lists, gather_states=h) for s in shards])
+    assert torch.equal(out, ref)
