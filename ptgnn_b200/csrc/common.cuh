@@ -121,5 +121,14 @@ __device__ __forceinline__ float apply_act(float x, int kind) {
     }
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate math of the tensor-core GRU epilogues (the epilogue warps are few, so instruction count per output matters).
+// fp32 path: ex2.approx exp (<= 2 ulp + |x| 2^-22 relative) and rcp.approx (1 ulp): sigmoid / tanh absolute error
+// <= ~3e-7, an order below the layer tolerance.  bf16 path: tanh.approx (one MUFU, relative error 2^-11), well inside
+// the bf16 rounding of the result.
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - 2.0f * rcp_approx(__expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 
 }  // namespace ptgnn

@@ -7,6 +7,7 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include "layers_tc.cuh"
 #include "tc_pipeline_bf16.cuh"
 
 namespace ptgnn {
@@ -52,6 +53,10 @@ __global__ void convert_weights_kernel(const __grid_constant__ ConvSrc s, __nv_b
         out[i] = __float2bfloat16_rn(s.w[i / s.elems][i % s.elems]);
 }
 // same gate-blocked layout as the fp32 path: P1[jb] = [W_ir; W_iz; W_in; 0], P2[jb] = [W_hr; W_hz; 0; W_hn] (128 rows each)
+__global__ void pack_gru_bias_bf16_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, int H, float4 *__restrict__ bias4) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < H) bias4[j] = make_float4(b_ih[j] + b_hh[j], b_ih[H + j] + b_hh[H + j], b_ih[2 * H + j], b_hh[2 * H + j]);
+}
 __global__ void pack_gru_bf16_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh, int H, int D,
                                      __nv_bfloat16 *__restrict__ p1, __nv_bfloat16 *__restrict__ p2) {
     const int nblk = H / 32;
@@ -77,22 +82,24 @@ struct MsgPolicyB {
         const __nv_bfloat16 *h;            // rows indexed by src32
         const int32_t *src32, *pos;
         __nv_bfloat16 *msg;                // [E, D] bf16 at target-sorted rows
-        int H, D, num_types, n_blocks;
+        unsigned long long *trace;
+        int H, D, num_types, n_blocks, dbg;   // dbg: PTGNN_TC_DEBUG ablation bits (1 no MMA, 2 no store, 4 no loads, 8 no drain)
         int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
         int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
     };
     struct Tile { int t, e0, e_end, n0, b_rows; };
     __device__ static int num_tiles(const Params &p) { return p.tile_off[p.num_types] * p.n_blocks; }
+    // Tiles are visited in increasing order by every role, so the edge type only ever moves forward from the previous
+    // tile's: an amortised O(1) walk over tile_off instead of a binary search of dependent constant loads per tile.
+    __device__ static void tile_init(Tile &ti) { ti.t = 0; }
     __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
-        const int mt = tile / p.n_blocks, nb = tile % p.n_blocks;
-        int lo = 0, hi = p.num_types - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (p.tile_off[mid] <= mt) lo = mid; else hi = mid - 1;
-        }
-        ti.t = lo;
-        ti.e0 = p.edge_off[lo] + (mt - p.tile_off[lo]) * TILE_M;
-        ti.e_end = p.edge_off[lo + 1];
+        int mt = tile, nb = 0;
+        if (p.n_blocks > 1) { mt = tile / p.n_blocks; nb = tile - mt * p.n_blocks; }
+        int t = ti.t;
+        while (p.tile_off[t + 1] <= mt) ++t;
+        ti.t = t;
+        ti.e0 = p.edge_off[t] + (mt - p.tile_off[t]) * TILE_M;
+        ti.e_end = p.edge_off[t + 1];
         ti.n0 = nb * 128;
         ti.b_rows = min(128, p.D - ti.n0);
     }
@@ -114,12 +121,15 @@ struct MsgPolicyB {
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
         drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
+    struct Pre { long long row_off; };
     // offsets are in 4-byte words of the bf16 message array (2 bf16 per word)
-    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+    __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int, int lane, Pre &pre) {
         const int e = ti.e0 + quarter * 32 + lane;
-        return e < ti.e_end ? ((long long)p.pos[e] * p.D + ti.n0) / 2 : -1;
+        pre.row_off = e < ti.e_end ? ((long long)p.pos[e] * p.D + ti.n0) / 2 : -1;
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off, int half, int lane, float *stage) {
+    __device__ static void smem_init(const Params &, float *) {}
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage, float *) {
+        const long long row_off = pre.row_off;
         const int c0 = 64 * half;            // this warp's 64 accumulator columns -> 32 packed words
         if (c0 >= ti.b_rows) return;
         float w[32];
@@ -137,15 +147,18 @@ struct GruPolicyB {
     struct Params {
         CUtensorMap map_agg, map_h, map_p1, map_p2;
         const __nv_bfloat16 *h;
-        const float *b_ih, *b_hh;
+        const float4 *bias4;   // (b_ir + b_hr, b_iz + b_hz, b_in, b_hn) per hidden unit
         __nv_bfloat16 *out;
-        int num_nodes, H, D, n_jb;
+        unsigned long long *trace;
+        int num_nodes, H, D, n_jb, dbg;
     };
     struct Tile { int row0, jb; };
     __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_jb; }
+    __device__ static void tile_init(Tile &) {}
     __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
-        ti.row0 = (tile / p.n_jb) * TILE_M;
-        ti.jb = tile % p.n_jb;
+        const int rb = tile / p.n_jb;
+        ti.row0 = rb * TILE_M;
+        ti.jb = tile - rb * p.n_jb;
     }
     __device__ static int num_segments(const Params &, const Tile &) { return 2; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
@@ -163,17 +176,28 @@ struct GruPolicyB {
     __device__ static void drain(const Params &, const Tile &, uint32_t tmem_lane, int half, float (&acc)[64]) {
         drain_4x16(tmem_lane, 16 * half, acc);
     }
-    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+    // a lane owns one node row and 16 hidden units of it: 32 bytes (one sector) of h in, 32 bytes of h' out
+    struct Pre { long long off; uint4 h0, h1; };
+    __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int half, int lane, Pre &pre) {
         const int row = ti.row0 + quarter * 32 + lane;
-        return row < p.num_nodes ? ((long long)row * p.H + ti.jb * 32) / 2 : -1;   // 4-byte words
+        pre.off = row < p.num_nodes ? (long long)row * p.H + ti.jb * 32 + 16 * half : -1;   // bf16 elements
+        pre.h0 = pre.h1 = make_uint4(0u, 0u, 0u, 0u);
+        if (pre.off >= 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.h + pre.off);
+            pre.h0 = __ldg(src);
+            pre.h1 = __ldg(src + 1);
+        }
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off0, int half, int lane, float *stage) {
-        const int H = p.H;
+    // the epilogue's transpose buffers are unused by this policy (a lane stores its own 32 bytes): they hold bias4
+    __device__ static void smem_init(const Params &p, float *tables) {
+        float4 *b = reinterpret_cast<float4 *>(tables);
+        for (int j = threadIdx.x; j < p.H; j += blockDim.x) b[j] = p.bias4[j];
+    }
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int, float *, float *tables) {
+        const float4 *bias_s = reinterpret_cast<const float4 *>(tables);
         const int j0 = ti.jb * 32 + 16 * half;
-        const long long row_off = row_off0 < 0 ? -1 : row_off0 + 8 * half;
-        float hw[8];                                                               // 16 bf16 = 8 words of h[row][j0 .. j0+16)
-        tc::warp_load_rows<8>(stage, hw, reinterpret_cast<const float *>(p.h), row_off, lane);
-        float ow[8];
+        const uint32_t hw[8] = {pre.h0.x, pre.h0.y, pre.h0.z, pre.h0.w, pre.h1.x, pre.h1.y, pre.h1.z, pre.h1.w};
+        uint32_t ow[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const __nv_bfloat162 hp = *reinterpret_cast<const __nv_bfloat162 *>(&hw[i]);
@@ -181,15 +205,21 @@ struct GruPolicyB {
             float o[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int ii = 2 * i + u, j = j0 + ii;
-                const float rr = sigmoid_f(acc[ii] + (p.b_ih[j] + p.b_hh[j]));
-                const float zz = sigmoid_f(acc[16 + ii] + (p.b_ih[H + j] + p.b_hh[H + j]));
-                const float nn = tanhf(acc[32 + ii] + p.b_ih[2 * H + j] + rr * (acc[48 + ii] + p.b_hh[2 * H + j]));
-                o[u] = (1.0f - zz) * nn + zz * hv[u];
+                const int ii = 2 * i + u;
+                const float4 b = (p.dbg & 16) ? make_float4(0.1f, 0.2f, 0.3f, 0.4f) : bias_s[j0 + ii];
+                if (p.dbg & 32) { o[u] = acc[ii] + acc[16 + ii] + acc[32 + ii] + acc[48 + ii] + b.x + hv[u]; continue; }
+                const float rr = sigmoid_mufu(acc[ii] + b.x);
+                const float zz = sigmoid_mufu(acc[16 + ii] + b.y);
+                const float nn = tanh_mufu(fmaf(rr, acc[48 + ii] + b.w, acc[32 + ii] + b.z));
+                o[u] = fmaf(zz, hv[u] - nn, nn);
             }
-            ow[i] = pack_bf16x2(o[0], o[1]);
+            ow[i] = __float_as_uint(pack_bf16x2(o[0], o[1]));
         }
-        tc::warp_store_rows<8>(stage, ow, reinterpret_cast<float *>(p.out), row_off, lane);
+        if (pre.off >= 0 && !(p.dbg & 64)) {
+            uint4 *dst = reinterpret_cast<uint4 *>(p.out + pre.off);
+            dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        }
     }
 };
 
@@ -288,6 +318,10 @@ static int launch_reduce_bf16(const __nv_bfloat16 *msg, const int32_t *row_ptr, 
     return PTGNN_OK;
 }
 
+static int debug_bits() {
+    const char *e = getenv("PTGNN_TC_DEBUG");
+    return e ? atoi(e) : 0;
+}
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -313,7 +347,7 @@ static int launch_pipeline(const typename Policy::Params &p, int total_tiles, in
     return PTGNN_OK;
 }
 
-struct WsB { size_t msg, agg, w, p1, p2, total; };
+struct WsB { size_t msg, agg, w, p1, p2, bias, total; };
 static WsB ws_layout(int64_t N, int64_t E, int T, int H, int D) {
     WsB w{};
     size_t o = 0;
@@ -323,6 +357,7 @@ static WsB ws_layout(int64_t N, int64_t E, int T, int H, int D) {
     w.w = add((size_t)T * D * H + 8);
     w.p1 = add((size_t)(H / 32 + 1) * 128 * D);
     w.p2 = add((size_t)(H / 32 + 1) * 128 * H);
+    w.bias = add((size_t)H * 8 + 8);
     w.total = o;
     return w;
 }
@@ -384,6 +419,12 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
         pack_gru_bf16_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, p1, p2);
     }
     PTGNN_LAUNCHED();
+    float4 *bias4 = reinterpret_cast<float4 *>(ws + L.bias);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_gru_bias_bf16_kernel<<<(H + 127) / 128, 128, 0, st>>>(gru_b_ih, gru_b_hh, H, bias4);
+    }
+    PTGNN_LAUNCHED();
 
     // 1. messages
     MsgPolicyB::Params mp{};
@@ -391,6 +432,7 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     if (rc) return rc;
     mp.h = hsrc; mp.src32 = src32; mp.pos = pos; mp.msg = msg; mp.H = H; mp.D = D; mp.num_types = num_types;
     mp.n_blocks = (D + 127) / 128;
+    mp.dbg = debug_bits(); mp.trace = tc::trace_buffer(PTGNN_KERNEL_MESSAGE + 10);
     int tiles = 0;
     for (int t = 0; t < num_types; ++t) {
         mp.edge_off[t] = (int32_t)type_off[t];
@@ -418,7 +460,7 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     if (!rc) rc = make_map_bf16(&gp.map_p1, p1, prow, D, 128);
     if (!rc) rc = make_map_bf16(&gp.map_p2, p2, prow, H, 128);
     if (rc) return rc;
-    gp.h = h; gp.b_ih = gru_b_ih; gp.b_hh = gru_b_hh; gp.out = reinterpret_cast<__nv_bfloat16 *>(out_states);
-    gp.num_nodes = (int)num_nodes; gp.H = H; gp.D = D; gp.n_jb = H / 32;
+    gp.h = h; gp.bias4 = bias4; gp.out = reinterpret_cast<__nv_bfloat16 *>(out_states);
+    gp.num_nodes = (int)num_nodes; gp.H = H; gp.D = D; gp.n_jb = H / 32; gp.dbg = debug_bits(); gp.trace = tc::trace_buffer(PTGNN_KERNEL_GRU + 10);
     return launch_pipeline<GruPolicyB>(gp, (int)ceil_div(num_nodes, TILE_M) * gp.n_jb, PTGNN_KERNEL_GRU, st);
 }

@@ -66,6 +66,12 @@ __global__ void split_weights_kernel(const __grid_constant__ SplitSrc s, float *
 //   P1[jb][n][k], n in [0,128):  [W_ir ; W_iz ; W_in ; 0   ]   (weight_ih rows, k < D)   accumulator cols r | z | i_n | h_n
 //   P2[jb][n][k], n in [0,128):  [W_hr ; W_hz ; 0    ; W_hn]   (weight_hh rows, k < H)
 // The zero blocks make the input GEMM clear the h_n columns and leave i_n untouched by the hidden GEMM.
+// bias4[j] = (b_ir + b_hr, b_iz + b_hz, b_in, b_hn): one 16-byte load per hidden unit in the epilogue
+__global__ void pack_gru_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, int H, float4 *__restrict__ bias4) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < H) bias4[j] = make_float4(b_ih[j] + b_hh[j], b_ih[H + j] + b_hh[H + j], b_ih[2 * H + j], b_hh[2 * H + j]);
+}
+
 __global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh, int H, int D,
                                       float *__restrict__ p1_hi, float *__restrict__ p1_lo, float *__restrict__ p2_hi,
                                       float *__restrict__ p2_lo) {
@@ -162,7 +168,7 @@ struct GruPolicy {
         CUtensorMap map_agg, map_h;                              // [N, D], [N, H], box {32, 128}
         CUtensorMap map_p1_hi, map_p1_lo, map_p2_hi, map_p2_lo;  // [n_jb*128, D] / [n_jb*128, H], box {32, 128}
         const float *h;
-        const float *b_ih, *b_hh;
+        const float4 *bias4;
         float *out;
         int num_nodes, H, D, n_jb, dbg;
         unsigned long long *trace;
@@ -211,12 +217,13 @@ struct GruPolicy {
         warp_load_rows<16>(stage, hval, p.h, row_off, lane);   // h[row][j0 .. j0+16), coalesced
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int j = j0 + i;
-            const float rr = sigmoid_f(acc[i] + (p.b_ih[j] + p.b_hh[j]));
-            const float zz = sigmoid_f(acc[16 + i] + (p.b_ih[H + j] + p.b_hh[H + j]));
-            const float nn = tanhf(acc[32 + i] + p.b_ih[2 * H + j] + rr * (acc[48 + i] + p.b_hh[2 * H + j]));
+            const float4 b = p.bias4[j0 + i];
+            const float rr = sigmoid_fast(acc[i] + b.x);
+            const float zz = sigmoid_fast(acc[16 + i] + b.y);
+            const float nn = tanh_fast(acc[32 + i] + b.z + rr * (acc[48 + i] + b.w));
             hval[i] = (1.0f - zz) * nn + zz * hval[i];
         }
+        (void)H;
         warp_store_rows<16>(stage, hval, p.out, row_off, lane);
     }
 };
@@ -315,7 +322,7 @@ static int mode_override() {
 // PTGNN_TC_TRACE=<category>: timeline trace of CTA 0 for launches of that kernel category; read it back with
 // ptgnn_b200_debug_trace() (debug only, not part of the public header).
 static unsigned long long *g_trace_dev = nullptr;
-static unsigned long long *trace_buffer(int category) {
+unsigned long long *trace_buffer(int category) {
     static int want = -2;
     if (want == -2) { const char *e = getenv("PTGNN_TC_TRACE"); want = e ? atoi(e) : -1; }
     if (want != category) return nullptr;
@@ -350,7 +357,7 @@ static int launch_pipeline(typename Policy::Params &p, int total_tiles, int cate
 }
 
 size_t split_edge_weights_bytes(int num_types, int D, int Kw) { return 2 * ws_slice((size_t)num_types * D * Kw, 4); }
-size_t gru_pack_bytes(int H, int D) { return 2 * ws_slice((size_t)(H / 32) * 128 * D, 4) + 2 * ws_slice((size_t)(H / 32) * 128 * H, 4); }
+size_t gru_pack_bytes(int H, int D) { return 2 * ws_slice((size_t)(H / 32) * 128 * D, 4) + 2 * ws_slice((size_t)(H / 32) * 128 * H, 4) + ws_slice((size_t)H * 4, 4); }
 size_t dense_split_bytes(int Hout, int D) { return 2 * ws_slice((size_t)Hout * D, 4); }
 
 bool supported_message(int H, int D) { return H % 4 == 0 && D % 16 == 0 && H >= 32 && D >= 16; }
@@ -394,9 +401,15 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
     const size_t s1 = ws_slice((size_t)(H / 32) * 128 * D, 4), s2 = ws_slice((size_t)(H / 32) * 128 * H, 4);
     float *p1_hi = reinterpret_cast<float *>(s), *p1_lo = reinterpret_cast<float *>(s + s1);
     float *p2_hi = reinterpret_cast<float *>(s + 2 * s1), *p2_lo = reinterpret_cast<float *>(s + 2 * s1 + s2);
+    float4 *bias4 = reinterpret_cast<float4 *>(s + 2 * s1 + 2 * s2);
     {
         TimedScope timed__(PTGNN_KERNEL_PACK, st);
         pack_split_gru_kernel<<<148, 256, 0, st>>>(w_ih, w_hh, H, D, p1_hi, p1_lo, p2_hi, p2_lo);
+    }
+    PTGNN_LAUNCHED();
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_gru_bias_kernel<<<(H + 127) / 128, 128, 0, st>>>(b_ih, b_hh, H, bias4);
     }
     PTGNN_LAUNCHED();
     GruPolicy::Params p{};
@@ -408,7 +421,7 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
     if (!rc) rc = make_map_2d(&p.map_p2_hi, p2_hi, prow, H, H, 128);
     if (!rc) rc = make_map_2d(&p.map_p2_lo, p2_lo, prow, H, H, 128);
     if (rc) return rc;
-    p.h = h; p.b_ih = b_ih; p.b_hh = b_hh;
+    p.h = h; p.bias4 = bias4;
     p.out = out; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = H / 32;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_jb;
     return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, true, st);

@@ -12,6 +12,8 @@ bool supported_dense(int D, int Hout);
 
 size_t split_edge_weights_bytes(int num_types, int D, int Kw);
 size_t gru_pack_bytes(int H, int D);
+// debug: device buffer for a CTA-0 timeline when PTGNN_TC_TRACE == category (else nullptr); bf16 kernels use category + 10
+unsigned long long *trace_buffer(int category);
 size_t dense_split_bytes(int Hout, int D);
 
 // messages[pos[e]] = W_t(e) [h_src[src(e)] ; h_tgt[tgt(e)]]   (scratch >= split_edge_weights_bytes)

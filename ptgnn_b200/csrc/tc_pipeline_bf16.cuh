@@ -8,7 +8,7 @@
 //                        fence.proxy.async + arrive on full[slot] once this thread's pieces have landed
 //   warp  4    MMA       one thread: wait full[slot] + landed[slot]; K/16 MMAs (A, B from shared memory, SWIZZLE_128B
 //                        K-major descriptors); tcgen05.commit -> empty[slot]; per tile commit -> tmem_full[acc]
-//   warps 8-15 EPILOGUE  drain the fp32 accumulator (two warps per TMEM lane quarter), release it, policy store
+//   warps 8-15 EPILOGUE  two sets of four warps on alternate tiles: drain the fp32 accumulator, release it, policy store
 //   shared memory: 6 slots x 32 KB (A 128 rows x 64 bf16 | B <= 128 rows x 64 bf16) + 32 KB transpose buffers
 //   tensor memory: 2 accumulator sets x 128 fp32 columns (MMAs of tile i+1 overlap the epilogue of tile i)
 #pragma once
@@ -61,20 +61,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_SLOTS; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); mbar_init(&landed[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS / 2); }
         tc::mbar_init_fence();
     }
     if (warp == 0) tc::tmem_alloc<256>(tmem_base_smem);
+    Policy::smem_init(p, stage_base);          // policy-owned tables in the staging area (e.g. the GRU biases)
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_base_smem;
     const int total_tiles = Policy::num_tiles(p);
+    unsigned long long *trace_base = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
 
     if (warp < 4) {
         // =========================================== LOADERS ===========================================
         tc::reg_dealloc<LOADER_REGS>();
         const int q = lane & 7, rsub = warp * 32 + (lane >> 3);
+        tc::Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0};
         constexpr int PPT = 8;
         struct Cursor { int tile, seg, kc; };
         typename Policy::Tile t_load, t_pref, t_proc;
@@ -111,6 +114,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
                               ? reinterpret_cast<const unsigned char *>(sg_load.a + (size_t)rows_load[i] * sg_load.lda) + q * 16
                               : nullptr;
         };
+        Policy::tile_init(t_load);
+        Policy::tile_init(t_proc);
         if (load_valid) {
             Policy::tile_setup(p, cl.tile, t_load);
             sg_load = Policy::segment(p, t_load, 0);
@@ -124,17 +129,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
 
         auto issue = [&]() {
             const uint32_t slot = c_load % NUM_SLOTS, use = c_load / NUM_SLOTS;
+            tr.mark(1);
             mbar_wait(&empty[slot], (use & 1) ^ 1);
+            tr.mark(2);
             unsigned char *base = ring + slot * SLOT_BYTES;
             const Segment &sg = sg_load;
             const int kchunk = cl.kc * CHUNK_K;
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 0 && !(p.dbg & 4)) {
                 const uint32_t bytes = (uint32_t)sg.b_box_rows * 128u + (sg.a_map ? (uint32_t)OPERAND_BYTES : 0u);
                 tc::mbar_expect_tx(&landed[slot], bytes);
                 if (sg.a_map) tc::tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
                 tc::tma_load_2d(base + OPERAND_BYTES, sg.b_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
             }
-            if (sg.a_map == nullptr) {
+            if (sg.a_map == nullptr && !(p.dbg & 4)) {
                 const bool k_ok = kchunk + q * 8 < sg.K;
                 const uint32_t sbase = smem_u32(base);
 #pragma unroll
@@ -164,9 +171,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
             cp_async_commit();
         }
         while (proc_valid) {
+            tr.mark(3);
             cp_async_wait<LOOKAHEAD - 1>();           // this thread's gathered pieces of chunk c_proc have landed
             tc::fence_proxy_async_smem();             // ... and are visible to the tensor core (async proxy)
+            tr.mark(4);
             mbar_arrive(&full[c_proc % NUM_SLOTS]);
+            tr.mark(6);
             ++c_proc;
             if (load_valid) issue();
             cp_async_commit();
@@ -183,10 +193,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
         if (warp == 4 && lane == 0) {
             uint32_t c = 0, tcount = 0;
             typename Policy::Tile t;
+            tc::Tracer tr{trace_base ? trace_base + 2048 : nullptr, 0};
+            Policy::tile_init(t);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                tr.mark(10);
                 Policy::tile_setup(p, tile, t);
                 const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
                 mbar_wait(&tmem_empty[acc], (acc_use & 1) ^ 1);
+                tr.mark(12);
                 tc::tc_fence_after_sync();
                 const uint32_t tmem_acc = tmem_base + acc * 128;
                 const int nseg = Policy::num_segments(p, t);
@@ -197,8 +211,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
                     const int nkc = (sg.K + CHUNK_K - 1) / CHUNK_K;
                     for (int kc = 0; kc < nkc; ++kc, ++c) {
                         const uint32_t slot = c % NUM_SLOTS, use = c / NUM_SLOTS;
+                        tr.mark(13);
                         mbar_wait(&full[slot], use & 1);
-                        mbar_wait(&landed[slot], use & 1);
+                        tr.mark(14);
+                        if (!(p.dbg & 4)) mbar_wait(&landed[slot], use & 1);
+                        tr.mark(16);
                         tc::tc_fence_after_sync();
                         const uint32_t base = smem_u32(ring + slot * SLOT_BYTES);
                         const int ksteps = (min(CHUNK_K, sg.K - kc * CHUNK_K) + 15) / 16;
@@ -212,10 +229,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
                                 const uint32_t acc0 = (g[gi].fresh && kc == 0) ? 0u : 1u;
 #pragma unroll
                                 for (int ks = 0; ks < CHUNK_K / 16; ++ks)
-                                    if (ks < ksteps) tc::mma_bf16_ss(d, a0 + ks * 2, b0 + ks * 2, idesc, ks == 0 ? acc0 : 1u);
+                                    if (ks < ksteps && !(p.dbg & 1)) tc::mma_bf16_ss(d, a0 + ks * 2, b0 + ks * 2, idesc, ks == 0 ? acc0 : 1u);
                             }
                         }
                         tc::mma_commit(&empty[slot]);
+                        tr.mark(15);
                     }
                 }
                 tc::mma_commit(&tmem_full[acc]);
@@ -224,24 +242,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
         __syncwarp();
     } else {
         // =========================================== EPILOGUE ===========================================
+        // Two sets of four warps (one warp per TMEM lane quarter) take alternate tiles -- set s owns accumulator s.  The
+        // per-tile chain (wait, tcgen05.ld, transpose, stores queued behind the loaders' traffic) is latency-bound, so
+        // two tiles in flight per CTA double the epilogue rate; a warp covers its 32 rows in two 64-column passes.
         tc::reg_alloc<EPI_REGS>();
-        const int ew = warp - 8, quarter = warp & 3, half = ew >> 2;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int ew = warp - 8, quarter = warp & 3, set = ew >> 2;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * 128;
         float *stage = stage_base + ew * (STAGE_BYTES_PER_WARP / 4);
-        uint32_t tcount = 0;
-        typename Policy::Tile t;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        typename Policy::Tile t, t_next;
+        // Everything the store needs from global memory (destination offsets, the GRU's h values) is fetched one tile
+        // ahead: a load issued when the accumulator is ready would queue behind the loaders' requests.
+        typename Policy::Pre pre[2], pre_next[2];
+        tc::Tracer tr{(trace_base && ew == 0 && lane == 0) ? trace_base + 4096 : nullptr, 0};
+        const int stride = 2 * gridDim.x;
+        int tile = blockIdx.x + set * gridDim.x;
+        Policy::tile_init(t);
+        if (tile < total_tiles) {
             Policy::tile_setup(p, tile, t);
-            const long long row_off = Policy::store_row_offset(p, t, quarter, lane);
-            const uint32_t acc = tcount & 1, acc_use = tcount >> 1;
-            mbar_wait(&tmem_full[acc], acc_use & 1);
+            Policy::prefetch(p, t, quarter, 0, lane, pre[0]);
+            Policy::prefetch(p, t, quarter, 1, lane, pre[1]);
+        }
+        for (uint32_t use = 0; tile < total_tiles; tile += stride, ++use) {
+            const int next = tile + stride;
+            if (next < total_tiles) {
+                t_next = t;
+                Policy::tile_setup(p, next, t_next);
+                Policy::prefetch(p, t_next, quarter, 0, lane, pre_next[0]);
+                Policy::prefetch(p, t_next, quarter, 1, lane, pre_next[1]);
+            }
+            tr.mark(20);
+            mbar_wait(&tmem_full[set], use & 1);
+            tr.mark(21);
             tc::tc_fence_after_sync();
-            float v[64];
-            Policy::drain(p, t, tmem_lane + acc * 128, half, v);
-            tc::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            Policy::store(p, t, v, row_off, half, lane, stage);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[64];
+                if (!(p.dbg & 8)) Policy::drain(p, t, tmem_lane, pass, v);
+                if (pass == 1) {
+                    tc::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[set]);
+                    tr.mark(22);
+                }
+                if (!(p.dbg & 2)) Policy::store(p, t, v, pre[pass], pass, lane, stage, stage_base);
+            }
+            tr.mark(23);
+            t = t_next;
+            pre[0] = pre_next[0];
+            pre[1] = pre_next[1];
         }
     }
     tc::tc_fence_before_sync();

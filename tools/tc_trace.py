@@ -7,6 +7,8 @@ from ptgnn_b200 import _native as N
 batch = bench.make_batch("graph2class")
 gnn = bench.build_model(17, "sum").cuda()
 h = torch.randn(batch.num_nodes, 128).cuda()
+if os.environ.get("TRACE_DTYPE") == "bf16":
+    h = h.bfloat16()
 adj = [(s.cuda(), t.cuda()) for s, t in batch.adjacency_lists]
 ident = torch.arange(batch.num_nodes, device="cuda")
 ex = list(adj) + [(t, s) for s, t in adj] + [(ident, ident)]
@@ -17,7 +19,7 @@ lib = ctypes.CDLL(N.LIB_PATH)
 buf = np.zeros(3 * 2048, dtype=np.uint64)
 assert lib.ptgnn_b200_debug_trace(buf.ctypes.data_as(ctypes.c_void_p)) == 1
 names = {1: "P issue:enter", 2: "P issue:empty ok", 3: "P proc:enter", 4: "P cp.async ok", 5: "P landed ok", 6: "P full arrived",
-         10: "M tile", 11: "M setup done", 12: "M tmem_empty ok", 13: "M wait full", 14: "M full ok", 15: "M committed",
+         10: "M tile", 11: "M setup done", 12: "M tmem_empty ok", 13: "M wait full", 14: "M full ok", 16: "M landed ok", 15: "M committed",
          20: "E wait tmem_full", 21: "E tmem_full ok", 22: "E drained+released", 23: "E stored"}
 ev = []
 for r in range(3):
