@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 3 * NUM_SLOTS + 4);
     float *stage_base = reinterpret_cast<float *>(ring + RING_BYTES + 128);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_SLOTS; ++s) {
             mbar_init(&full[s], PRODUCER_THREADS);   // producers: A converted into TMEM (and B landed)
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_base_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_smem, 0);
     const int total_tiles = Policy::num_tiles(p);
     // timing experiments only (PTGNN_TC_DEBUG; results are wrong when set): 1 = no MMAs, 2 = no loads, 4 = no stores,
     // 8 = no A conversion
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
         Cursor cl{(int)blockIdx.x, 0, 0}, cpf{(int)blockIdx.x, 0, 0}, cp{(int)blockIdx.x, 0, 0};
         bool load_valid = cl.tile < total_tiles, pref_valid = false, proc_valid = load_valid;
         uint32_t c_load = 0, c_proc = 0;
-        Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0};
+        const bool tma_leader = warp == 0 && elect_one();   // issues the bulk tensor copies (uniform operands, no R2UR waterfall)
+        Tracer tr{(trace_base && tma_leader) ? trace_base : nullptr, 0};
 
         // (tile, seg) that follows `c`; returns false past the end
         auto advance_seg = [&](Cursor &c, typename Policy::Tile &t) -> bool {
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             unsigned char *base = ring + slot * SLOT_BYTES;
             const Segment &sg = sg_load;
             const int kchunk = cl.kc * CHUNK_K;
-            if (threadIdx.x == 0) {   // bulk tensor copies: weights (hi, lo) and, for contiguous rows, the raw A tile
+            if (tma_leader) {   // bulk tensor copies: weights (hi, lo) and, for contiguous rows, the raw A tile
                 if (dbg & 2) {
                     mbar_arrive(&landed[slot]);
                 } else {
@@ -392,9 +394,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     } else if (warp < FIRST_EPI_WARP) {
         // =========================================== MMA ISSUER (warp 4; warps 5-7 only give their registers away) ========
         reg_dealloc<MMA_REGS>();
-        if (warp == MMA_WARP && lane == 0) {
+        if (warp == MMA_WARP) {
+            // The whole warp walks the loop converged (every lane polls the barriers) and one elected lane issues: the
+            // descriptors then live in uniform registers.  Issued from an `if (lane == 0)` region every tcgen05.mma was
+            // wrapped in an ELECT / R2UR.BROADCAST waterfall loop, ~100 cycles per instruction.
+            const bool leader = elect_one();
             uint32_t c = 0, tcount = 0;
-            Tracer tr{trace_base ? trace_base + 2048 : nullptr, 0};
+            Tracer tr{(trace_base && leader) ? trace_base + 2048 : nullptr, 0};
             typename Policy::Tile t;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 tr.mark(10);
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                                 const uint32_t acc0 = (g[gi].fresh && kc == 0) ? 0u : 1u;
 #pragma unroll
                                 for (int ks = 0; ks < CHUNK_K / 8; ++ks) {
-                                    if (ks < ksteps) {
+                                    if (ks < ksteps && leader) {
                                         const uint32_t first = ks == 0 ? acc0 : 1u;
                                         if constexpr (TS) {
                                             mma_tf32_ts(d_main, a_buf + ks * 8, b_hi0 + ks * 2, idesc, first);
@@ -449,14 +455,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                                 }
                             }
                         }
-                        mma_commit(&empty[slot]);
+                        if (leader) mma_commit(&empty[slot]);
+                        __syncwarp();
                         tr.mark(15);
                     }
                 }
-                mma_commit(&tmem_full[acc]);
+                if (leader) mma_commit(&tmem_full[acc]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // =========================================== EPILOGUE ===========================================
         reg_alloc<EPI_REGS>();

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 3 * NUM_SLOTS + 4);
     float *stage_base = reinterpret_cast<float *>(ring + RING_BYTES + 256);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_SLOTS; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); mbar_init(&landed[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS / 2); }
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_base_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_smem, 0);
     const int total_tiles = Policy::num_tiles(p);
     unsigned long long *trace_base = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
 
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
         // =========================================== LOADERS ===========================================
         tc::reg_dealloc<LOADER_REGS>();
         const int q = lane & 7, rsub = warp * 32 + (lane >> 3);
-        tc::Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0};
+        const bool tma_leader = warp == 0 && tc::elect_one();   // issues the bulk tensor copies (uniform operands)
+        tc::Tracer tr{(trace_base && tma_leader) ? trace_base : nullptr, 0};
         constexpr int PPT = 8;
         struct Cursor { int tile, seg, kc; };
         typename Policy::Tile t_load, t_pref, t_proc;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
             unsigned char *base = ring + slot * SLOT_BYTES;
             const Segment &sg = sg_load;
             const int kchunk = cl.kc * CHUNK_K;
-            if (threadIdx.x == 0 && !(p.dbg & 4)) {
+            if (tma_leader && !(p.dbg & 4)) {
                 const uint32_t bytes = (uint32_t)sg.b_box_rows * 128u + (sg.a_map ? (uint32_t)OPERAND_BYTES : 0u);
                 tc::mbar_expect_tx(&landed[slot], bytes);
                 if (sg.a_map) tc::tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
@@ -190,10 +192,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
     } else if (warp < 8) {
         // =========================================== MMA ISSUER ===========================================
         tc::reg_dealloc<MMA_REGS>();
-        if (warp == 4 && lane == 0) {
+        if (warp == 4) {
+            // the whole warp walks the loop converged (all lanes poll the barriers); one elected lane issues
+            const bool leader = tc::elect_one();
             uint32_t c = 0, tcount = 0;
             typename Policy::Tile t;
-            tc::Tracer tr{trace_base ? trace_base + 2048 : nullptr, 0};
+            tc::Tracer tr{(trace_base && leader) ? trace_base + 2048 : nullptr, 0};
             Policy::tile_init(t);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 tr.mark(10);
@@ -229,17 +233,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
                                 const uint32_t acc0 = (g[gi].fresh && kc == 0) ? 0u : 1u;
 #pragma unroll
                                 for (int ks = 0; ks < CHUNK_K / 16; ++ks)
-                                    if (ks < ksteps && !(p.dbg & 1)) tc::mma_bf16_ss(d, a0 + ks * 2, b0 + ks * 2, idesc, ks == 0 ? acc0 : 1u);
+                                    if (ks < ksteps && !(p.dbg & 1) && leader) tc::mma_bf16_ss(d, a0 + ks * 2, b0 + ks * 2, idesc, ks == 0 ? acc0 : 1u);
                             }
                         }
-                        tc::mma_commit(&empty[slot]);
+                        if (leader) tc::mma_commit(&empty[slot]);
+                        __syncwarp();
                         tr.mark(15);
                     }
                 }
-                tc::mma_commit(&tmem_full[acc]);
+                if (leader) tc::mma_commit(&tmem_full[acc]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // =========================================== EPILOGUE ===========================================
         // Two sets of four warps (one warp per TMEM lane quarter) take alternate tiles -- set s owns accumulator s.  The
