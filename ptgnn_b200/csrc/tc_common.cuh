@@ -106,6 +106,14 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Tell the compiler a value is the same in every lane (broadcast from lane 0): it may then live in a uniform register.
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+template <class T> __device__ __forceinline__ const T *warp_uniform(const T *ptr) {
+    const unsigned long long v = reinterpret_cast<unsigned long long>(ptr);
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0);
+    return reinterpret_cast<const T *>(((unsigned long long)hi << 32) | lo);
+}
 // One lane of a converged warp (the same one every time).  Issuing tcgen05.mma / commit under this predicate from a warp
 // that runs the whole loop converged lets the compiler keep descriptors in uniform registers; issuing them from an
 // `if (lane == 0)` region makes it wrap every MMA in an ELECT / R2UR.BROADCAST waterfall loop (~100 cycles per MMA).

@@ -45,10 +45,11 @@ namespace tc {
 constexpr int TILE_M = 128;
 constexpr int CHUNK_K = 32;                       // fp32 per k-chunk = one 128-byte swizzled row
 // Warp roles, in warpgroups of 4 so that setmaxnreg can move registers from the light roles to the epilogue:
-//   WG0 = warps 0-3 producers (120 regs) | WG1 = warp 4 MMA issuer, warps 5-7 idle (40) | WG2+WG3 = warps 8-15 epilogue (176)
+//   WG0 = warps 0-3 producers (120 regs) | WG1 = warp 4 MMA issuer, warp 5 TMA issuer, warps 6-7 idle (40) | WG2+WG3 = warps 8-15 epilogue (176)
 constexpr int NUM_PRODUCER_WARPS = 4;
 constexpr int PRODUCER_THREADS = NUM_PRODUCER_WARPS * 32;
 constexpr int MMA_WARP = 4;
+constexpr int TMA_WARP = 5;
 constexpr int FIRST_EPI_WARP = 8;
 constexpr int NUM_EPI_WARPS = 8;                  // two per TMEM lane quarter, each draining half of the columns
 constexpr int NUM_THREADS = 16 * 32;
@@ -250,8 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
         Cursor cl{(int)blockIdx.x, 0, 0}, cpf{(int)blockIdx.x, 0, 0}, cp{(int)blockIdx.x, 0, 0};
         bool load_valid = cl.tile < total_tiles, pref_valid = false, proc_valid = load_valid;
         uint32_t c_load = 0, c_proc = 0;
-        const bool tma_leader = warp == 0 && elect_one();   // issues the bulk tensor copies (uniform operands, no R2UR waterfall)
-        Tracer tr{(trace_base && tma_leader) ? trace_base : nullptr, 0};
+        Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0};
 
         // (tile, seg) that follows `c`; returns false past the end
         auto advance_seg = [&](Cursor &c, typename Policy::Tile &t) -> bool {
@@ -289,23 +289,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
 
         auto issue = [&]() {   // stage chunk (cl) into slot c_load % NUM_SLOTS
             const uint32_t slot = c_load % NUM_SLOTS, use = c_load / NUM_SLOTS;
-            tr.mark(1);
-            mbar_wait(&empty[slot], (use & 1) ^ 1);
-            tr.mark(2);
             unsigned char *base = ring + slot * SLOT_BYTES;
             const Segment &sg = sg_load;
             const int kchunk = cl.kc * CHUNK_K;
-            if (tma_leader) {   // bulk tensor copies: weights (hi, lo) and, for contiguous rows, the raw A tile
-                if (dbg & 2) {
-                    mbar_arrive(&landed[slot]);
-                } else {
-                    const uint32_t bytes = 2u * (uint32_t)sg.b_box_rows * 128u + (sg.a_map ? (uint32_t)OPERAND_BYTES : 0u);
-                    mbar_expect_tx(&landed[slot], bytes);
-                    if (sg.a_map) tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
-                    tma_load_2d(base + M::B_HI_OFF, sg.b_hi_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
-                    tma_load_2d(base + M::B_LO_OFF, sg.b_lo_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
-                }
-            }
+            tr.mark(1);
+            // gathered rows are staged by the producers themselves (the slot must be free first); contiguous A tiles and all
+            // weight tiles come from the TMA warp, which owns the `empty` wait for them
+            if (sg.a_map == nullptr) mbar_wait(&empty[slot], (use & 1) ^ 1);
+            tr.mark(2);
             if (sg.a_map == nullptr && !(dbg & 2)) {   // gathered rows
                 const bool k_ok = kchunk + q * 4 < sg.K;
                 const uint32_t sbase = smem_u32(base);
@@ -462,6 +453,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                 }
                 if (leader) mma_commit(&tmem_full[acc]);
                 __syncwarp();
+            }
+        } else if (warp == TMA_WARP) {
+            // =========================================== TMA WARP ===========================================
+            // Walks the same (tile, segment, k-chunk) sequence as the MMA warp, a whole ring ahead of it: waits for the
+            // slot's release, then issues the bulk tensor copies of the chunk -- weights (hi, lo) and, for contiguous rows,
+            // the raw A tile.  Converged warp + elected lane: all operands stay in uniform registers.
+            const bool leader = elect_one();
+            uint32_t c = 0;
+            typename Policy::Tile t;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                Policy::tile_setup(p, tile, t);
+                const int nseg = Policy::num_segments(p, t);
+                for (int seg = 0; seg < nseg; ++seg) {
+                    const Segment sg = Policy::segment(p, t, seg);
+                    const int nkc = (sg.K + CHUNK_K - 1) / CHUNK_K;
+                    const uint32_t bytes = 2u * (uint32_t)sg.b_box_rows * 128u + (sg.a_map != nullptr ? (uint32_t)OPERAND_BYTES : 0u);
+                    for (int kc = 0; kc < nkc; ++kc, ++c) {
+                        const uint32_t slot = c % NUM_SLOTS, use = c / NUM_SLOTS;
+                        mbar_wait(&empty[slot], (use & 1) ^ 1);
+                        unsigned char *base = ring + slot * SLOT_BYTES;
+                        const int kchunk = kc * CHUNK_K;
+                        const bool go = !(dbg & 2);
+                        if (!go && leader) mbar_arrive(&landed[slot]);
+                        if (go && leader) mbar_expect_tx(&landed[slot], bytes);
+                        if (go && sg.a_map != nullptr && leader) tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
+                        if (go && leader) tma_load_2d(base + M::B_HI_OFF, sg.b_hi_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+                        if (go && leader) tma_load_2d(base + M::B_LO_OFF, sg.b_lo_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+                        __syncwarp();
+                    }
+                }
             }
         }
     } else {

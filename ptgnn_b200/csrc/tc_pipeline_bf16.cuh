@@ -137,11 +137,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const 
             unsigned char *base = ring + slot * SLOT_BYTES;
             const Segment &sg = sg_load;
             const int kchunk = cl.kc * CHUNK_K;
-            if (tma_leader && !(p.dbg & 4)) {
-                const uint32_t bytes = (uint32_t)sg.b_box_rows * 128u + (sg.a_map ? (uint32_t)OPERAND_BYTES : 0u);
-                tc::mbar_expect_tx(&landed[slot], bytes);
-                if (sg.a_map) tc::tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
-                tc::tma_load_2d(base + OPERAND_BYTES, sg.b_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+            if (warp == 0) {   // single predicated statements on warp-uniform operands: no R2UR waterfall around the TMA issue
+                const bool go = !(p.dbg & 4);
+                const CUtensorMap *am = tc::warp_uniform(sg.a_map), *bm = tc::warp_uniform(sg.b_map);
+                const int a_row0 = tc::warp_uniform(sg.a_row0), b_row0 = tc::warp_uniform(sg.b_row0);
+                const int b_col = tc::warp_uniform(sg.b_col0 + kchunk), a_col = tc::warp_uniform(kchunk);
+                const uint32_t bytes = tc::warp_uniform((uint32_t)sg.b_box_rows * 128u + (am != nullptr ? (uint32_t)OPERAND_BYTES : 0u));
+                if (go && tma_leader) tc::mbar_expect_tx(&landed[slot], bytes);
+                if (go && am != nullptr && tma_leader) tc::tma_load_2d(base, am, a_col, a_row0, &landed[slot]);
+                if (go && tma_leader) tc::tma_load_2d(base + OPERAND_BYTES, bm, b_col, b_row0, &landed[slot]);
             }
             if (sg.a_map == nullptr && !(p.dbg & 4)) {
                 const bool k_ok = kchunk + q * 8 < sg.K;
