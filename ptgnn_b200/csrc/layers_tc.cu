@@ -61,11 +61,12 @@ __global__ void split_weights_kernel(const __grid_constant__ SplitSrc s, float *
         lo[i] = x - h;
     }
 }
-// Gate-blocked GRU weights, 32 hidden units per block jb, 128 rows per block so that ONE N = 128 MMA per K-step serves
-// both GEMMs of the cell (tcgen05 instructions cost ~100 cycles regardless of N: fewer, wider MMAs win over exact N):
-//   P1[jb][n][k], n in [0,128):  [W_ir ; W_iz ; W_in ; 0   ]   (weight_ih rows, k < D)   accumulator cols r | z | i_n | h_n
-//   P2[jb][n][k], n in [0,128):  [W_hr ; W_hz ; 0    ; W_hn]   (weight_hh rows, k < H)
-// The zero blocks make the input GEMM clear the h_n columns and leave i_n untouched by the hidden GEMM.
+// Gate-blocked GRU weights, 32 hidden units per block jb, 128 rows per block:
+//   P1[jb][n][k], n in [0,128):  [W_in ; W_ir ; W_iz ; 0   ]   (weight_ih rows, k < D)   accumulator cols i_n | r | z | h_n
+//   P2[jb][n][k], n in [0,128):  [0    ; W_hr ; W_hz ; W_hn]   (weight_hh rows, k < H)
+// One MMA per K-step per GEMM, N = 96: rows [0,96) of P1 -> columns [0,96), rows [32,128) of P2 -> columns [32,128).  Only
+// the very first K-step of a tile runs N = 128 over P1 (its zero block clears the h_n columns).  The MMA time is
+// proportional to N now that the issue is not the limit, so the zero blocks are not multiplied any more.
 // bias4[j] = (b_ir + b_hr, b_iz + b_hz, b_in, b_hn): one 16-byte load per hidden unit in the epilogue
 __global__ void pack_gru_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, int H, float4 *__restrict__ bias4) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -80,15 +81,16 @@ __global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const floa
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < n1) {
             const int k = (int)(i % D), n = (int)((i / D) % 128), jb = (int)(i / ((int64_t)128 * D));
-            const int gate = n / 32;   // 0 r, 1 z, 2 i_n, 3 zero
-            const float x = gate < 3 ? w_ih[(size_t)(gate * H + jb * 32 + n % 32) * D + k] : 0.0f;
+            const int blk = n / 32;    // 0 i_n, 1 r, 2 z, 3 zero        (weight_ih gate order is r, z, n)
+            const int gate = blk == 0 ? 2 : blk - 1;
+            const float x = blk < 3 ? w_ih[(size_t)(gate * H + jb * 32 + n % 32) * D + k] : 0.0f;
             const float h = tf32_hi(x);
             p1_hi[i] = h; p1_lo[i] = x - h;
         } else {
             const int64_t r = i - n1;
             const int k = (int)(r % H), n = (int)((r / H) % 128), jb = (int)(r / ((int64_t)128 * H));
-            const int gate = n / 32;   // 0 r, 1 z, 2 zero, 3 h_n
-            const float x = gate == 2 ? 0.0f : w_hh[(size_t)((gate == 3 ? 2 : gate) * H + jb * 32 + n % 32) * H + k];
+            const int blk = n / 32;    // 0 zero, 1 r, 2 z, 3 h_n
+            const float x = blk == 0 ? 0.0f : w_hh[(size_t)((blk - 1) * H + jb * 32 + n % 32) * H + k];
             const float h = tf32_hi(x);
             p2_hi[r] = h; p2_lo[r] = x - h;
         }
@@ -112,16 +114,17 @@ struct MsgPolicy {
     struct Tile { int t, e0, e_end, n0, b_rows; };
 
     __device__ static int num_tiles(const Params &p) { return p.tile_off[p.num_types] * p.n_blocks; }
+    // Every role visits its tiles in increasing order, so the edge type only moves forward from the previous tile's: an
+    // amortised O(1) walk over tile_off instead of a binary search of dependent constant loads per tile.
+    __device__ static void tile_init(Tile &ti) { ti.t = 0; }
     __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
-        const int mt = tile / p.n_blocks, nb = tile % p.n_blocks;
-        int lo = 0, hi = p.num_types - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (p.tile_off[mid] <= mt) lo = mid; else hi = mid - 1;
-        }
-        ti.t = lo;
-        ti.e0 = p.edge_off[lo] + (mt - p.tile_off[lo]) * TILE_M;
-        ti.e_end = p.edge_off[lo + 1];
+        int mt = tile, nb = 0;
+        if (p.n_blocks > 1) { mt = tile / p.n_blocks; nb = tile - mt * p.n_blocks; }
+        int t = ti.t;
+        while (p.tile_off[t + 1] <= mt) ++t;
+        ti.t = t;
+        ti.e0 = p.edge_off[t] + (mt - p.tile_off[t]) * TILE_M;
+        ti.e_end = p.edge_off[t + 1];
         ti.n0 = nb * 128;
         ti.b_rows = min(128, p.D - ti.n0);
     }
@@ -139,18 +142,20 @@ struct MsgPolicy {
         return seg == 0 ? p.src32[e] : p.tgt32[e];
     }
     __device__ static int mma_groups(const Params &, const Tile &ti, int seg, MmaGroup (&g)[2]) {
-        g[0] = MmaGroup{ti.b_rows, 0, 0, seg == 0};
+        g[0] = MmaGroup{ti.b_rows, 0, 0, seg == 0, 0};
         return 1;
     }
     // warp `half` owns accumulator columns [64*half, 64*half + 64)
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
         tmem_drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
-    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+    struct Pre { long long row_off; };
+    __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int, int lane, Pre &pre) {
         const int e = ti.e0 + quarter * 32 + lane;
-        return e < ti.e_end ? (long long)p.pos[e] * p.D + ti.n0 : -1;
+        pre.row_off = e < ti.e_end ? (long long)p.pos[e] * p.D + ti.n0 : -1;
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off, int half, int lane, float *stage) {
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage) {
+        const long long row_off = pre.row_off;
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
             const int c0 = 64 * half + 32 * cb;
@@ -176,9 +181,11 @@ struct GruPolicy {
     struct Tile { int row0, jb; };
 
     __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_jb; }
+    __device__ static void tile_init(Tile &) {}
     __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
-        ti.row0 = (tile / p.n_jb) * TILE_M;   // jb fastest: the CTAs that share a row tile run at the same time (L2 reuse)
-        ti.jb = tile % p.n_jb;
+        const int rb = tile / p.n_jb;         // jb fastest: the CTAs that share a row tile run at the same time (L2 reuse)
+        ti.row0 = rb * TILE_M;
+        ti.jb = tile - rb * p.n_jb;
     }
     __device__ static int num_segments(const Params &, const Tile &) { return 2; }
     __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
@@ -196,35 +203,44 @@ struct GruPolicy {
         return row < p.num_nodes ? row : -1;
     }
     __device__ static int mma_groups(const Params &, const Tile &, int seg, MmaGroup (&g)[2]) {
-        // seg 0: [r z i_n h_n] = agg x [W_ir W_iz W_in 0]^T (fresh);  seg 1: += h x [W_hr W_hz 0 W_hn]^T
-        g[0] = MmaGroup{128, 0, 0, seg == 0};
+        // seg 0: [i_n r z] += agg x [W_in W_ir W_iz]^T, N = 96; its very first K-step runs N = 128 over the zero block of
+        //        P1 so that it also clears the h_n columns.   seg 1: [r z h_n] += h x [W_hr W_hz W_hn]^T, N = 96.
+        if (seg == 0) g[0] = MmaGroup{96, 0, 0, true, 128};
+        else g[0] = MmaGroup{96, 32, 32, false, 0};
         return 1;
     }
-    // accumulator columns: [0,32) r | [32,64) z | [64,96) i_n | [96,128) h_n (pre-activations without biases);
+    // accumulator columns: [0,32) i_n | [32,64) r | [64,96) z | [96,128) h_n (pre-activations without biases);
     // warp `half` owns hidden units j0 + 16*half .. +16 and therefore 16 columns of each gate group
     __device__ static void drain(const Params &, const Tile &, uint32_t tmem_lane, int half, float (&acc)[64]) {
         tmem_drain_4x16(tmem_lane, 16 * half, acc);
     }
-    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+    // a lane owns one node row and 16 hidden units of it: 64 bytes of h, fetched one tile ahead
+    struct Pre { long long row_off; float4 h[4]; };
+    __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int half, int lane, Pre &pre) {
         const int row = ti.row0 + quarter * 32 + lane;
-        return row < p.num_nodes ? (long long)row * p.H + ti.jb * 32 : -1;
+        pre.row_off = row < p.num_nodes ? (long long)row * p.H + ti.jb * 32 + 16 * half : -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pre.h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pre.row_off >= 0) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.h + pre.row_off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pre.h[i] = __ldg(src + i);
+        }
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off0, int half, int lane, float *stage) {
-        const int H = p.H;
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage) {
         const int j0 = ti.jb * 32 + 16 * half;
-        const long long row_off = row_off0 < 0 ? -1 : row_off0 + 16 * half;
         float hval[16];
-        warp_load_rows<16>(stage, hval, p.h, row_off, lane);   // h[row][j0 .. j0+16), coalesced
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hval[4 * i] = pre.h[i].x; hval[4 * i + 1] = pre.h[i].y; hval[4 * i + 2] = pre.h[i].z; hval[4 * i + 3] = pre.h[i].w; }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float4 b = p.bias4[j0 + i];
-            const float rr = sigmoid_fast(acc[i] + b.x);
-            const float zz = sigmoid_fast(acc[16 + i] + b.y);
-            const float nn = tanh_fast(acc[32 + i] + b.z + rr * (acc[48 + i] + b.w));
+            const float rr = sigmoid_fast(acc[16 + i] + b.x);
+            const float zz = sigmoid_fast(acc[32 + i] + b.y);
+            const float nn = tanh_fast(acc[i] + b.z + rr * (acc[48 + i] + b.w));
             hval[i] = (1.0f - zz) * nn + zz * hval[i];
         }
-        (void)H;
-        warp_store_rows<16>(stage, hval, p.out, row_off, lane);
+        warp_store_rows<16>(stage, hval, p.out, pre.row_off, lane);
     }
 };
 
@@ -242,6 +258,7 @@ struct DensePolicy {
     struct Tile { int row0, n0, b_rows; };
 
     __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_blocks; }
+    __device__ static void tile_init(Tile &) {}
     __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
         ti.row0 = (tile / p.n_blocks) * TILE_M;
         ti.n0 = (tile % p.n_blocks) * 128;
@@ -259,17 +276,19 @@ struct DensePolicy {
         return row < p.num_nodes ? row : -1;
     }
     __device__ static int mma_groups(const Params &, const Tile &ti, int, MmaGroup (&g)[2]) {
-        g[0] = MmaGroup{ti.b_rows, 0, 0, true};
+        g[0] = MmaGroup{ti.b_rows, 0, 0, true, 0};
         return 1;
     }
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
         tmem_drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
-    __device__ static long long store_row_offset(const Params &p, const Tile &ti, int quarter, int lane) {
+    struct Pre { long long row_off; };
+    __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int, int lane, Pre &pre) {
         const int row = ti.row0 + quarter * 32 + lane;
-        return row < p.num_nodes ? (long long)row * p.Hout + ti.n0 : -1;
+        pre.row_off = row < p.num_nodes ? (long long)row * p.Hout + ti.n0 : -1;
     }
-    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], long long row_off, int half, int lane, float *stage) {
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage) {
+        const long long row_off = pre.row_off;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
             const int c0 = 64 * half + 16 * cb;

@@ -32,8 +32,10 @@
 //   __device__ static int  mma_groups(const Params&, const Tile&, int seg, MmaGroup (&g)[2]);
 //   __device__ static void drain(const Params&, const Tile&, uint32_t tmem_lane, int half, float (&acc)[64]);
 //                          (read this warp's share of main + correction accumulators; tmem_ld_sum16/32 below)
-//   __device__ static long long store_row_offset(const Params&, const Tile&, int quarter, int lane);   (-1 = row not stored)
-//   __device__ static void store(const Params&, const Tile&, float (&acc)[64], long long row_off, int half, int lane, float* stage);
+//   __device__ static void tile_init(Tile&);   tiles are set up in increasing order per role: tile_setup may walk forward
+//   struct Pre;  __device__ static void prefetch(const Params&, const Tile&, int quarter, int half, int lane, Pre&);
+//                          (global-memory inputs of the store -- row offset (-1 = row not stored), GRU h -- one tile ahead)
+//   __device__ static void store(const Params&, const Tile&, float (&acc)[64], const Pre&, int half, int lane, float* stage);
 #pragma once
 #include <cuda.h>
 
@@ -89,6 +91,8 @@ struct Segment {        // one K-range of the tile's GEMM
 struct MmaGroup {       // per K-step: B rows [row_off, row_off + n) -> accumulator columns [col_off, col_off + n)
     int n, row_off, col_off;
     bool fresh;         // true: the first K-step of this segment overwrites the accumulator columns
+    int n_first;        // width of that first (overwriting) K-step; > n lets it also clear columns that a later segment
+                        // accumulates into (the GRU's h_n block) -- 0 means n
 };
 
 __device__ __forceinline__ uint32_t swz(int row, int q) { return (uint32_t)(row * 128 + ((q ^ (row & 7)) << 4)); }
@@ -275,6 +279,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             for (int i = 0; i < PPT; ++i)
                 rowp[i] = (sg_load.a_map == nullptr && rows_load[i] >= 0) ? sg_load.a + (size_t)rows_load[i] * sg_load.lda + q * 4 : nullptr;
         };
+        Policy::tile_init(t_load);
+        Policy::tile_init(t_proc);
         if (load_valid) {
             Policy::tile_setup(p, cl.tile, t_load);
             sg_load = Policy::segment(p, t_load, 0);
@@ -393,6 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             uint32_t c = 0, tcount = 0;
             Tracer tr{(trace_base && leader) ? trace_base + 2048 : nullptr, 0};
             typename Policy::Tile t;
+            Policy::tile_init(t);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 tr.mark(10);
                 Policy::tile_setup(p, tile, t);
@@ -426,13 +433,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                             if (gi < ng) {
                                 const uint64_t b_hi0 = make_smem_desc_sw128(base + M::B_HI_OFF + g[gi].row_off * 128);
                                 const uint64_t b_lo0 = make_smem_desc_sw128(base + M::B_LO_OFF + g[gi].row_off * 128);
-                                const uint32_t idesc = make_instr_desc(FMT_TF32, TILE_M, (uint32_t)g[gi].n);
+                                const uint32_t idesc_n = make_instr_desc(FMT_TF32, TILE_M, (uint32_t)g[gi].n);
                                 const uint32_t d_main = tmem_acc + g[gi].col_off, d_corr = d_main + CORR_OFF;
-                                const uint32_t acc0 = (g[gi].fresh && kc == 0) ? 0u : 1u;
+                                const bool overwrite = g[gi].fresh && kc == 0;
+                                const uint32_t acc0 = overwrite ? 0u : 1u;
+                                const uint32_t idesc_first = (overwrite && g[gi].n_first > 0)
+                                                                 ? make_instr_desc(FMT_TF32, TILE_M, (uint32_t)g[gi].n_first) : idesc_n;
 #pragma unroll
                                 for (int ks = 0; ks < CHUNK_K / 8; ++ks) {
                                     if (ks < ksteps && leader) {
                                         const uint32_t first = ks == 0 ? acc0 : 1u;
+                                        const uint32_t idesc = ks == 0 ? idesc_first : idesc_n;
                                         if constexpr (TS) {
                                             mma_tf32_ts(d_main, a_buf + ks * 8, b_hi0 + ks * 2, idesc, first);
                                             mma_tf32_ts(d_corr, a_buf + ks * 8, b_lo0 + ks * 2, idesc, first);
@@ -462,6 +473,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             const bool leader = elect_one();
             uint32_t c = 0;
             typename Policy::Tile t;
+            Policy::tile_init(t);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 Policy::tile_setup(p, tile, t);
                 const int nseg = Policy::num_segments(p, t);
@@ -495,10 +507,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
         float *stage = stage_base + ew * (STAGE_BYTES_PER_WARP / 4);
         uint32_t tcount = 0;
         Tracer tr{(trace_base && ew == 0 && lane == 0) ? trace_base + 4096 : nullptr, 0};
-        typename Policy::Tile t;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        typename Policy::Tile t, t_next;
+        // What the store needs from global memory (destination offsets, the GRU's h values) is fetched one tile ahead: the
+        // epilogue is a serial per-tile chain and a load issued at store time queues behind the producers' gathers.
+        typename Policy::Pre pre, pre_next;
+        int tile = blockIdx.x;
+        Policy::tile_init(t);
+        if (tile < total_tiles) {
             Policy::tile_setup(p, tile, t);
-            const long long row_off = Policy::store_row_offset(p, t, quarter, lane);   // issued before the wait: latency hidden
+            Policy::prefetch(p, t, quarter, half, lane, pre);
+        }
+        for (; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int next = tile + gridDim.x;
+            if (next < total_tiles) {
+                t_next = t;
+                Policy::tile_setup(p, next, t_next);
+                Policy::prefetch(p, t_next, quarter, half, lane, pre_next);
+            }
             const uint32_t aset = tcount % M::NUM_ACC, aset_use = tcount / M::NUM_ACC;
             tr.mark(20);
             mbar_wait_warp(&tmem_full[aset], aset_use & 1, lane);
@@ -510,8 +535,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[aset]);   // this accumulator set may be overwritten while we store
             tr.mark(22);
-            if (!(dbg & 4)) Policy::store(p, t, acc, row_off, half, lane, stage);
+            if (!(dbg & 4)) Policy::store(p, t, acc, pre, half, lane, stage);
             tr.mark(23);
+            t = t_next;
+            pre = pre_next;
         }
     }
     tc_fence_before_sync();

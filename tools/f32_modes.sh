@@ -1,6 +1,6 @@
 #!/bin/bash
 # fp32 bench in both tcgen05 operand modes (TS = A from tensor memory, SS = A hi/lo from shared memory)
-for m in ts ss; do
+for m in ${MODES:-ts ss}; do
   echo "== mode $m"
   PTGNN_TC_MODE=$m timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
