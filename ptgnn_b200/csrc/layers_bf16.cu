@@ -121,15 +121,17 @@ struct MsgPolicyB {
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
         drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
-    struct Pre { long long row_off; };
-    // offsets are in 4-byte words of the bf16 message array (2 bf16 per word)
+    // only the raw load is issued a tile ahead: arithmetic on the loaded value would stall the in-order issue right there
+    struct Pre { int32_t pos; };
     __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int, int lane, Pre &pre) {
         const int e = ti.e0 + quarter * 32 + lane;
-        pre.row_off = e < ti.e_end ? ((long long)p.pos[e] * p.D + ti.n0) / 2 : -1;
+        pre.pos = -1;
+        if (e < ti.e_end) pre.pos = __ldg(p.pos + e);
     }
     __device__ static void smem_init(const Params &, float *) {}
     __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage, float *) {
-        const long long row_off = pre.row_off;
+        // offsets are in 4-byte words of the bf16 message array (2 bf16 per word)
+        const long long row_off = pre.pos >= 0 ? ((long long)pre.pos * p.D + ti.n0) / 2 : -1;
         const int c0 = 64 * half;            // this warp's 64 accumulator columns -> 32 packed words
         if (c0 >= ti.b_rows) return;
         float w[32];

@@ -101,6 +101,7 @@ __global__ void pack_split_gru_kernel(const float *__restrict__ w_ih, const floa
 // policy 1: per-edge messages  (gather -> W_t -> row scattered to its target-sorted position)
 // =================================================================================================
 struct MsgPolicy {
+    static constexpr bool GATHER = true;
     struct Params {
         CUtensorMap map_w_hi, map_w_lo;   // [T*D, Kw], box {32, min(128, D)}
         const float *h, *h_tgt;           // rows indexed by src32 / by tgt32
@@ -149,13 +150,15 @@ struct MsgPolicy {
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
         tmem_drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
     }
-    struct Pre { long long row_off; };
+    // only the raw load is issued a tile ahead: any arithmetic on the loaded value would stall the in-order issue right there
+    struct Pre { int32_t pos; };
     __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int, int lane, Pre &pre) {
         const int e = ti.e0 + quarter * 32 + lane;
-        pre.row_off = e < ti.e_end ? (long long)p.pos[e] * p.D + ti.n0 : -1;
+        pre.pos = -1;
+        if (e < ti.e_end) pre.pos = __ldg(p.pos + e);
     }
     __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage) {
-        const long long row_off = pre.row_off;
+        const long long row_off = pre.pos >= 0 ? (long long)pre.pos * p.D + ti.n0 : -1;
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
             const int c0 = 64 * half + 32 * cb;
@@ -169,6 +172,7 @@ struct MsgPolicy {
 // policy 2: nn.GRUCell update, 32 hidden units per tile:  columns [0,32) r | [32,64) z | [64,96) i_n | [96,128) h_n
 // =================================================================================================
 struct GruPolicy {
+    static constexpr bool GATHER = false;
     struct Params {
         CUtensorMap map_agg, map_h;                              // [N, D], [N, H], box {32, 128}
         CUtensorMap map_p1_hi, map_p1_lo, map_p2_hi, map_p2_lo;  // [n_jb*128, D] / [n_jb*128, H], box {32, 128}
@@ -248,6 +252,7 @@ struct GruPolicy {
 // policy 3: Mlp dense update   out = act(y W^T + b)
 // =================================================================================================
 struct DensePolicy {
+    static constexpr bool GATHER = false;
     struct Params {
         CUtensorMap map_y, map_w_hi, map_w_lo;   // [N, D] box {32,128}; [Hout, D] box {32, min(128, Hout)}
         const float *bias;
@@ -328,16 +333,6 @@ static int debug_flags() {
     return v;
 }
 
-// Operand staging mode per kernel (see Mode<> in tc_pipeline.cuh); PTGNN_TC_MODE=ss|ts overrides the default for A/B runs.
-static int mode_override() {
-    static int v = -2;
-    if (v == -2) {
-        const char *e = getenv("PTGNN_TC_MODE");
-        v = !e ? -1 : (e[0] == 't' ? 1 : 0);
-    }
-    return v;
-}
-
 // PTGNN_TC_TRACE=<category>: timeline trace of CTA 0 for launches of that kernel category; read it back with
 // ptgnn_b200_debug_trace() (debug only, not part of the public header).
 static unsigned long long *g_trace_dev = nullptr;
@@ -350,29 +345,23 @@ unsigned long long *trace_buffer(int category) {
     return g_trace_dev;
 }
 
-template <class Policy, bool TS>
-static int launch_mode(typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
+template <class Policy>
+static int launch_pipeline(typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
+    if (total_tiles <= 0) return PTGNN_OK;
+    p.dbg = debug_flags();
+    p.trace = trace_buffer(category);
     static bool configured = false;
     if (!configured) {
-        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_kernel<Policy, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mode<TS>::SMEM_BYTES));
+        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
     {
         TimedScope timed__(category, st);
-        tc_pipeline_kernel<Policy, TS><<<grid, NUM_THREADS, Mode<TS>::SMEM_BYTES, st>>>(p);
+        tc_pipeline_kernel<Policy><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
-}
-
-template <class Policy>
-static int launch_pipeline(typename Policy::Params &p, int total_tiles, int category, bool ts_default, cudaStream_t st) {
-    if (total_tiles <= 0) return PTGNN_OK;
-    p.dbg = debug_flags();
-    p.trace = trace_buffer(category);
-    const bool ts = mode_override() < 0 ? ts_default : mode_override() == 1;
-    return ts ? launch_mode<Policy, true>(p, total_tiles, category, st) : launch_mode<Policy, false>(p, total_tiles, category, st);
 }
 
 size_t split_edge_weights_bytes(int num_types, int D, int Kw) { return 2 * ws_slice((size_t)num_types * D * Kw, 4); }
@@ -411,7 +400,7 @@ int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_
         tiles += (int)ceil_div(type_off[t + 1] - type_off[t], TILE_M);
     }
     for (int t = num_types; t <= PTGNN_MAX_EDGE_TYPES; ++t) { p.edge_off[t] = (int32_t)type_off[num_types]; p.tile_off[t] = tiles; }
-    return launch_pipeline<MsgPolicy>(p, tiles * p.n_blocks, PTGNN_KERNEL_MESSAGE, true, st);
+    return launch_pipeline<MsgPolicy>(p, tiles * p.n_blocks, PTGNN_KERNEL_MESSAGE, st);
 }
 
 int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D, const float *w_ih, const float *w_hh,
@@ -443,7 +432,7 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
     p.h = h; p.bias4 = bias4;
     p.out = out; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = H / 32;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_jb;
-    return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, true, st);
+    return launch_pipeline<GruPolicy>(p, tiles, PTGNN_KERNEL_GRU, st);
 }
 
 int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const float *bias, int Hout, int act, float *out,
@@ -465,7 +454,7 @@ int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const
     p.bias = bias; p.out = out; p.num_nodes = (int)num_nodes; p.D = D; p.Hout = Hout;
     p.act = act; p.n_blocks = (Hout + 127) / 128;
     const int tiles = (int)ceil_div(num_nodes, TILE_M) * p.n_blocks;
-    return launch_pipeline<DensePolicy>(p, tiles, PTGNN_KERNEL_DENSE, true, st);
+    return launch_pipeline<DensePolicy>(p, tiles, PTGNN_KERNEL_DENSE, st);
 }
 
 }  // namespace tc

@@ -1,34 +1,39 @@
 // Persistent, warp-specialised tcgen05 pipeline shared by the three GEMM-bearing kernels of the hot path
 // (per-edge messages, GRUCell update, Mlp dense update).  fp32-exact via 3xTF32 (see tc_common.cuh).
 //
-//   warps 0-3  PRODUCERS  stage the raw fp32 A tile (128 rows x 32 k) in shared memory -- gathered node-state rows via
-//                         cp.async (per-edge messages) or one TMA tile (contiguous node rows) -- and the pre-split
-//                         weight tile (hi, lo) via TMA.  Each producer thread then owns ONE row: it reads its 32
-//                         floats, splits them into TF32 hi/lo and writes both into TENSOR MEMORY (tcgen05.st), so
-//                         the MMAs take A from TMEM ("TS" form) and shared memory only feeds B.
-//   warp  4    MMA        one thread: wait full[slot]; per K=8 step issue hi*hi into the MAIN accumulator and
-//                         hi*lo + lo*hi into the CORRECTION accumulator (tensor-core accumulation truncates, so the
-//                         small terms must not perturb the main sum); tcgen05.commit -> empty[slot]; per tile
-//                         commit -> tmem_full.
+//   warps 0-3  CONVERTERS each thread owns ONE row of every chunk: it reads its 32 raw fp32 from the slot, splits them into
+//                         TF32 hi/lo and writes both into TENSOR MEMORY (tcgen05.st), so the MMAs take A from TMEM ("TS"
+//                         form) and shared memory only feeds B.  The stores of chunk c stay in flight while the thread
+//                         waits for chunk c+1; then wait::st + arrive full[slot].
+//   warp  4    MMA        converged warp, one elected lane issues: wait full[slot]; per K=8 step hi*hi into the MAIN
+//                         accumulator and hi*lo + lo*hi into the CORRECTION accumulator (tensor-core accumulation
+//                         truncates, so the small terms must not perturb the main sum); tcgen05.commit -> empty[slot];
+//                         per tile commit -> tmem_full.
+//   warp  5    TMA        a ring ahead of the MMA warp: wait empty[slot]; bulk tensor copies of the pre-split weight tile
+//                         (hi, lo) and, for contiguous node rows, of the raw A tile -> landed[slot] (expect_tx).
+//   warps 6-7  GATHERERS  per-edge messages only: wait a_free[slot] (converters have read it); 16-byte cp.async (LDGSTS) of the gathered node-state
+//                         rows, completion signalled on landed[slot] by cp.async.mbarrier.arrive; row indices in shared
+//                         memory, fetched one (tile, segment) ahead.  ~53 GB/s per SM is the LDGSTS ceiling (probe in
+//                         tools/probes), 4x what TMA gather4 reaches -- and it needs its own warps to run at it.
 //   warps 8-15 EPILOGUE   wait tmem_full; drain main + correction into registers (row per thread, two warps per TMEM
-//                         lane quarter, half of the columns each); release the accumulator (tmem_empty) BEFORE the
+//                         lane quarter, half of the columns each); release the accumulators (tmem_empty) BEFORE the
 //                         policy's store phase (smem-transposed coalesced rows), so the next tile's MMAs overlap it.
 //
 // Why TS: an SS-mode tf32 MMA (128x128x8) reads 8 KB of operands from shared memory = the 64 cycles its math takes,
-// and the producers' traffic then starves it (measured: tensor pipe 17 % active).  With A in TMEM an MMA reads 4 KB.
+// and the staging traffic then starves it (measured: tensor pipe 17 % active).  With A in TMEM an MMA reads 4 KB.
 //
 // One CTA per SM (grid = #SMs), static round-robin over tiles.
-//   shared memory: 4 slots x 48 KB (raw A | B_hi | B_lo, 128-byte SWIZZLE_128B rows) + 16 KB epilogue transpose
+//   shared memory: 4 slots x 48 KB (raw A | B_hi | B_lo, 128-byte SWIZZLE_128B rows) + 1 KB row indices + 32 KB epilogue transpose
 //   tensor memory (512 columns): [0,128) main acc | [128,256) correction acc | [256,512) 4 x (A_hi 32 | A_lo 32)
 // Every mbarrier wait is bounded (tc_common.cuh): a protocol bug traps instead of hanging the GPU.
 //
 // A Policy supplies:
-//   struct Params;   struct Tile;
+//   struct Params;   struct Tile;   static constexpr bool GATHER;   (A rows gathered by index vs. contiguous TMA tiles)
 //   __device__ static int  num_tiles(const Params&);
 //   __device__ static void tile_setup(const Params&, int tile, Tile&);
 //   __device__ static int  num_segments(const Params&, const Tile&);
 //   __device__ static Segment segment(const Params&, const Tile&, int seg);
-//   __device__ static int  gather_row(const Params&, const Tile&, int seg, int r);   only when segment.a_map == nullptr
+//   __device__ static int  gather_row(const Params&, const Tile&, int seg, int r);   only when GATHER (then a_map == nullptr)
 //   __device__ static int  mma_groups(const Params&, const Tile&, int seg, MmaGroup (&g)[2]);
 //   __device__ static void drain(const Params&, const Tile&, uint32_t tmem_lane, int half, float (&acc)[64]);
 //                          (read this warp's share of main + correction accumulators; tmem_ld_sum16/32 below)
@@ -47,37 +52,32 @@ namespace tc {
 constexpr int TILE_M = 128;
 constexpr int CHUNK_K = 32;                       // fp32 per k-chunk = one 128-byte swizzled row
 // Warp roles, in warpgroups of 4 so that setmaxnreg can move registers from the light roles to the epilogue:
-//   WG0 = warps 0-3 producers (120 regs) | WG1 = warp 4 MMA issuer, warp 5 TMA issuer, warps 6-7 idle (40) | WG2+WG3 = warps 8-15 epilogue (176)
+//   WG0 = warps 0-3 converters (112 regs) | WG1 = warp 4 MMA issuer, warp 5 TMA issuer, warps 6-7 row gatherers (48)
+//   WG2+WG3 = warps 8-15 epilogue (176)
 constexpr int NUM_PRODUCER_WARPS = 4;
 constexpr int PRODUCER_THREADS = NUM_PRODUCER_WARPS * 32;
 constexpr int MMA_WARP = 4;
 constexpr int TMA_WARP = 5;
+constexpr int FIRST_GATHER_WARP = 6;
+constexpr int GATHER_THREADS = 64;
 constexpr int FIRST_EPI_WARP = 8;
 constexpr int NUM_EPI_WARPS = 8;                  // two per TMEM lane quarter, each draining half of the columns
 constexpr int NUM_THREADS = 16 * 32;
-constexpr int PRODUCER_REGS = 120, MMA_REGS = 40, EPI_REGS = 176;   // (120 + 40 + 176 + 176) * 128 = 65536
+constexpr int PRODUCER_REGS = 112, MMA_REGS = 48, EPI_REGS = 176;   // (112 + 48 + 176 + 176) * 128 = 65536
 constexpr int OPERAND_BYTES = TILE_M * CHUNK_K * 4;   // 16 KB: one 128 x 32 fp32 operand tile
 constexpr int STAGE_BYTES_PER_WARP = 32 * 32 * 4;     // epilogue transpose buffer: 32 rows x 32 fp32
 constexpr int CORR_OFF = 128;                         // correction accumulator columns (relative to the main ones)
 constexpr int A_TMEM_OFF = 256;                       // TS: A operand ring, slot s at columns A_TMEM_OFF + 64 s (hi | lo)
 
-// Two operand-staging modes (template parameter TS of the kernel):
-//   TS = true   A split into TMEM (tcgen05.st) -> MMAs read only B from shared memory; shared-memory ring 4 x 48 KB
-//               (raw A | B_hi | B_lo), loads issued 2 chunks ahead so the producer waits on the MMA of chunk c-2;
-//               TMEM = 256 accumulator columns (main + correction, single-buffered) + 256 columns of A.
-//   TS = false  A split in place in shared memory (A_hi | A_lo | B_hi | B_lo, ring 3 x 64 KB); TMEM = two accumulator
-//               sets of 256 columns, so the MMAs of tile i+1 overlap the whole epilogue of tile i.
-template <bool TS>
-struct Mode {
-    static constexpr int NUM_SLOTS = TS ? 4 : 3;
-    static constexpr int LOOKAHEAD = 2;
-    static constexpr int SLOT_BYTES = (TS ? 3 : 4) * OPERAND_BYTES;
-    static constexpr int B_HI_OFF = (TS ? 1 : 2) * OPERAND_BYTES;
-    static constexpr int B_LO_OFF = (TS ? 2 : 3) * OPERAND_BYTES;
-    static constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
-    static constexpr int NUM_ACC = TS ? 1 : 2;
-    static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
-};
+// Shared-memory ring: 4 slots x 48 KB (raw A | B_hi | B_lo).  Tensor memory (512 columns): [0,128) main accumulator |
+// [128,256) correction accumulator | [256,512) 4 x (A_hi 32 | A_lo 32) -- the A operand of every MMA comes from TMEM.
+constexpr int NUM_SLOTS = 4;
+constexpr int SLOT_BYTES = 3 * OPERAND_BYTES;
+constexpr int B_HI_OFF = OPERAND_BYTES, B_LO_OFF = 2 * OPERAND_BYTES;
+constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
+constexpr int INDEX_BYTES = 2 * TILE_M * 4;           // gather warps: row indices of the current / next (tile, segment)
+constexpr int BARRIER_BYTES = 256;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + BARRIER_BYTES + INDEX_BYTES + NUM_EPI_WARPS * STAGE_BYTES_PER_WARP;
 
 struct Segment {        // one K-range of the tile's GEMM
     const float *a;     // gathered A rows (row pitch lda) -- used when a_map == nullptr
@@ -107,12 +107,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
 
-// Whole-warp wait.  (Electing one lane to poll was measured to be slower: try_wait is a warp-level instruction
-// anyway, and the divergence/reconvergence around the elected loop adds latency to every hand-off.)
-__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
-    (void)lane;
-    mbar_wait(bar, parity);
+// Arrive on `bar` (without raising its pending count) once all cp.async of the executing thread have completed.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // ---- epilogue transposes through shared memory ---------------------------------------------------------------
 // The accumulator comes out of TMEM one ROW per thread; storing that directly makes every warp-wide store touch 32
@@ -190,37 +189,43 @@ __device__ __forceinline__ void tmem_drain_4x16(uint32_t taddr, int off, float (
     }
 }
 
-// Optional timeline trace (PTGNN_TC_TRACE): CTA 0 records %globaltimer at pipeline hand-offs, 3 roles x 2048 slots.
+// Optional timeline trace (PTGNN_TC_TRACE): CTA 0 records %globaltimer at pipeline hand-offs into 3 x 2048 slots.
 struct Tracer {
     unsigned long long *buf;
-    int n;
+    int n, cap;
     __device__ __forceinline__ void mark(int tag) {
-        if (buf != nullptr && n < 2048) { buf[n++] = (global_timer_ns() << 8) | (unsigned long long)(tag & 0xFF); }
+        if (buf != nullptr && n < cap) { buf[n++] = (global_timer_ns() << 8) | (unsigned long long)(tag & 0xFF); }
     }
 };
 
-template <class Policy, bool TS>
+template <class Policy>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __grid_constant__ typename Policy::Params p) {
-    using M = Mode<TS>;
-    constexpr int NUM_SLOTS = M::NUM_SLOTS, LOOKAHEAD = M::LOOKAHEAD, SLOT_BYTES = M::SLOT_BYTES, RING_BYTES = M::RING_BYTES;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned ring (SWIZZLE_128B descriptors / TMA swizzle assume base_offset = 0)
     unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + RING_BYTES);
     uint64_t *full = bars, *empty = bars + NUM_SLOTS, *landed = bars + 2 * NUM_SLOTS;
-    uint64_t *tmem_full = bars + 3 * NUM_SLOTS, *tmem_empty = bars + 3 * NUM_SLOTS + 2;   // [NUM_ACC] each
-    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 3 * NUM_SLOTS + 4);
-    float *stage_base = reinterpret_cast<float *>(ring + RING_BYTES + 128);
+    uint64_t *a_free = bars + 3 * NUM_SLOTS;
+    uint64_t *tmem_full = bars + 4 * NUM_SLOTS, *tmem_empty = bars + 4 * NUM_SLOTS + 1;
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 4 * NUM_SLOTS + 2);
+    int32_t *index_buf = reinterpret_cast<int32_t *>(ring + RING_BYTES + BARRIER_BYTES);
+    float *stage_base = reinterpret_cast<float *>(ring + RING_BYTES + BARRIER_BYTES + INDEX_BYTES);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_SLOTS; ++s) {
-            mbar_init(&full[s], PRODUCER_THREADS);   // producers: A converted into TMEM (and B landed)
+            mbar_init(&full[s], PRODUCER_THREADS);   // converters: A of this chunk is in TMEM (hi | lo)
             mbar_init(&empty[s], 1);                 // MMA commit: smem slot + TMEM A buffer may be overwritten
-            mbar_init(&landed[s], 1);                // TMA bytes of this slot have landed
+            // operands of this chunk are in shared memory: the TMA warp's expect_tx arrival (+ its bytes) and, when A rows
+            // are gathered, one cp.async-completion arrival per gather thread
+            mbar_init(&landed[s], 1 + (Policy::GATHER ? GATHER_THREADS : 0));
+            // gathered rows only: the converters have read the slot's raw A tile -- the gatherers may refill it without
+            // waiting for the MMAs of the chunk (the MMAs read A from TMEM, only B from the slot)
+            mbar_init(&a_free[s], PRODUCER_THREADS);
         }
-        for (int a = 0; a < M::NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], NUM_EPI_WARPS); }
+        mbar_init(tmem_full, 1);                     // MMA commit: accumulators of the tile are complete
+        mbar_init(tmem_empty, NUM_EPI_WARPS);        // epilogue: accumulators drained
         mbar_init_fence();
     }
     if (warp == 0) tmem_alloc<512>(tmem_base_smem);
@@ -235,180 +240,85 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
     unsigned long long *trace_base = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
 
     if (warp < NUM_PRODUCER_WARPS) {
-        // =========================================== PRODUCERS ===========================================
-        // Warp w owns rows 32 w .. 32 w + 31.  It stages exactly the 16-byte pieces it converts afterwards: lane l -> piece
-        // q = l & 7 of rows r0 + (l >> 3) + 4 i, i < 8 (so only a __syncwarp separates staging and conversion), then
-        // thread `lane` converts row r0 + lane (all 32 floats of the chunk).
+        // =========================================== CONVERTERS ===========================================
+        // Thread r owns row r of every chunk: 32 raw fp32 from the slot -> TF32 hi / lo -> the slot's TMEM A buffer.  The
+        // tcgen05.st of chunk c is left in flight while the thread waits for chunk c+1 and reads its row; only then does it
+        // wait for the stores and hand chunk c to the MMA warp.
         reg_dealloc<PRODUCER_REGS>();
-        const int quarter = warp;
-        const int q = lane & 7, rsub = quarter * 32 + (lane >> 3);
-        const int my_row = quarter * 32 + lane;
-        constexpr int PPT = 8;   // pieces per thread
-        struct Cursor { int tile, seg, kc; };
-        typename Policy::Tile t_load, t_pref, t_proc;
-        Segment sg_load;
-        int rows_load[PPT], rows_pref[PPT];
-        const float *rowp[PPT];          // per (tile, segment): source pointer of this thread's pieces at k = 0 (nullptr = zero-fill)
-        uint32_t soff[PPT];              // swizzled shared-memory offsets of the pieces (constant per thread)
+        const int my_row = warp * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0, 1024};
+        uint32_t c = 0;
+        bool pending = false;
+        uint32_t pending_slot = 0;
+        typename Policy::Tile t;
+        Policy::tile_init(t);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            Policy::tile_setup(p, tile, t);
+            const int nseg = Policy::num_segments(p, t);
+            for (int seg = 0; seg < nseg; ++seg) {
+                const int nkc = (Policy::segment(p, t, seg).K + CHUNK_K - 1) / CHUNK_K;
+                for (int kc = 0; kc < nkc; ++kc, ++c) {
+                    const uint32_t slot = c % NUM_SLOTS, use = c / NUM_SLOTS;
+                    tr.mark(3);
+                    mbar_wait(&landed[slot], use & 1);
+                    tr.mark(5);
+                    const unsigned char *base = ring + slot * SLOT_BYTES;
+                    float4 raw[8];
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) soff[i] = swz(rsub + 4 * i, q);
-        Cursor cl{(int)blockIdx.x, 0, 0}, cpf{(int)blockIdx.x, 0, 0}, cp{(int)blockIdx.x, 0, 0};
-        bool load_valid = cl.tile < total_tiles, pref_valid = false, proc_valid = load_valid;
-        uint32_t c_load = 0, c_proc = 0;
-        Tracer tr{(trace_base && threadIdx.x == 0) ? trace_base : nullptr, 0};
-
-        // (tile, seg) that follows `c`; returns false past the end
-        auto advance_seg = [&](Cursor &c, typename Policy::Tile &t) -> bool {
-            ++c.seg;
-            c.kc = 0;
-            if (c.seg >= Policy::num_segments(p, t)) {
-                c.seg = 0;
-                c.tile += gridDim.x;
-                if (c.tile >= total_tiles) return false;
-                Policy::tile_setup(p, c.tile, t);
-            }
-            return true;
-        };
-        auto fetch_rows = [&](const typename Policy::Tile &t, int seg, int (&rows)[PPT]) {
-            if (Policy::segment(p, t, seg).a_map != nullptr) return;
+                    for (int j = 0; j < 8; ++j) raw[j] = *reinterpret_cast<const float4 *>(base + swz(my_row, j));
+                    if (pending) {
+                        tmem_st_wait();
+                        tc_fence_before_sync();
+                        mbar_arrive(&full[pending_slot]);
+                        tr.mark(6);
+                    }
+                    float hi[32], lo[32];
 #pragma unroll
-            for (int i = 0; i < PPT; ++i) rows[i] = Policy::gather_row(p, t, seg, rsub + 4 * i);
-        };
-        auto set_row_pointers = [&]() {
-#pragma unroll
-            for (int i = 0; i < PPT; ++i)
-                rowp[i] = (sg_load.a_map == nullptr && rows_load[i] >= 0) ? sg_load.a + (size_t)rows_load[i] * sg_load.lda + q * 4 : nullptr;
-        };
-        Policy::tile_init(t_load);
-        Policy::tile_init(t_proc);
-        if (load_valid) {
-            Policy::tile_setup(p, cl.tile, t_load);
-            sg_load = Policy::segment(p, t_load, 0);
-            fetch_rows(t_load, 0, rows_load);
-            set_row_pointers();
-            // gather indices of the NEXT (tile, segment) are fetched one step ahead: their ~1 us latency is off the path
-            t_pref = t_load; cpf = cl;
-            pref_valid = advance_seg(cpf, t_pref);
-            if (pref_valid) fetch_rows(t_pref, cpf.seg, rows_pref);
-        }
-        if (proc_valid) Policy::tile_setup(p, cp.tile, t_proc);
-
-        auto issue = [&]() {   // stage chunk (cl) into slot c_load % NUM_SLOTS
-            const uint32_t slot = c_load % NUM_SLOTS, use = c_load / NUM_SLOTS;
-            unsigned char *base = ring + slot * SLOT_BYTES;
-            const Segment &sg = sg_load;
-            const int kchunk = cl.kc * CHUNK_K;
-            tr.mark(1);
-            // gathered rows are staged by the producers themselves (the slot must be free first); contiguous A tiles and all
-            // weight tiles come from the TMA warp, which owns the `empty` wait for them
-            if (sg.a_map == nullptr) mbar_wait(&empty[slot], (use & 1) ^ 1);
-            tr.mark(2);
-            if (sg.a_map == nullptr && !(dbg & 2)) {   // gathered rows
-                const bool k_ok = kchunk + q * 4 < sg.K;
-                const uint32_t sbase = smem_u32(base);
-#pragma unroll
-                for (int i = 0; i < PPT; ++i) {
-                    const bool ok = k_ok && rowp[i] != nullptr;
-                    cp_async16(sbase + soff[i], ok ? (const void *)(rowp[i] + kchunk) : (const void *)sg.a, ok ? 16 : 0);
+                    for (int j = 0; j < 8; ++j) {
+                        hi[4 * j] = tf32_hi(raw[j].x); hi[4 * j + 1] = tf32_hi(raw[j].y);
+                        hi[4 * j + 2] = tf32_hi(raw[j].z); hi[4 * j + 3] = tf32_hi(raw[j].w);
+                        lo[4 * j] = raw[j].x - hi[4 * j]; lo[4 * j + 1] = raw[j].y - hi[4 * j + 1];
+                        lo[4 * j + 2] = raw[j].z - hi[4 * j + 2]; lo[4 * j + 3] = raw[j].w - hi[4 * j + 3];
+                    }
+                    if (Policy::GATHER) {
+                        mbar_arrive(&a_free[slot]);                       // raw tile consumed (values are in registers)
+                        mbar_wait(&empty[slot], (use & 1) ^ 1);           // TMEM A buffer of the slot: MMAs of chunk c-4 done
+                        tc_fence_after_sync();
+                    }
+                    const uint32_t a_buf = tmem_lane + A_TMEM_OFF + slot * 64;
+                    if (!(dbg & 8)) {
+                        tmem_st_32cols(a_buf, hi);
+                        tmem_st_32cols(a_buf + 32, lo);
+                    }
+                    pending = true;
+                    pending_slot = slot;
                 }
-            }
-            ++c_load;
-            ++cl.kc;
-            if (cl.kc * CHUNK_K >= sg.K) {   // move to the prefetched (tile, segment) and prefetch the one after it
-                load_valid = pref_valid;
-                if (load_valid) {
-                    cl = cpf; t_load = t_pref;
-                    sg_load = Policy::segment(p, t_load, cl.seg);
-#pragma unroll
-                    for (int i = 0; i < PPT; ++i) rows_load[i] = rows_pref[i];
-                    set_row_pointers();
-                    pref_valid = advance_seg(cpf, t_pref);
-                    if (pref_valid) fetch_rows(t_pref, cpf.seg, rows_pref);
-                }
-            }
-        };
-
-#pragma unroll
-        for (int i = 0; i < LOOKAHEAD; ++i) {
-            if (load_valid) issue();
-            cp_async_commit();
-        }
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        Segment sg_proc;
-        if (proc_valid) sg_proc = Policy::segment(p, t_proc, 0);
-        while (proc_valid) {
-            const uint32_t slot = c_proc % NUM_SLOTS, use = c_proc / NUM_SLOTS;
-            tr.mark(3);
-            cp_async_wait<LOOKAHEAD - 1>();          // this thread's gathered pieces of chunk c_proc
-            __syncwarp();                            // ... and those of the other lanes of this warp (same rows, same k-half)
-            tr.mark(4);
-            mbar_wait(&landed[slot], use & 1);       // TMA tiles of chunk c_proc
-            tr.mark(5);
-            unsigned char *base = ring + slot * SLOT_BYTES;
-            if constexpr (TS) {
-                // convert this thread's row: 32 raw floats -> TF32 hi / lo -> TMEM columns of the slot's A buffer
-                float hi[32], lo[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 v = *reinterpret_cast<const float4 *>(base + swz(my_row, j));
-                    hi[4 * j] = tf32_hi(v.x); hi[4 * j + 1] = tf32_hi(v.y); hi[4 * j + 2] = tf32_hi(v.z); hi[4 * j + 3] = tf32_hi(v.w);
-                    lo[4 * j] = v.x - hi[4 * j]; lo[4 * j + 1] = v.y - hi[4 * j + 1];
-                    lo[4 * j + 2] = v.z - hi[4 * j + 2]; lo[4 * j + 3] = v.w - hi[4 * j + 3];
-                }
-                const uint32_t a_buf = tmem_lane + A_TMEM_OFF + slot * 64;
-                if (!(dbg & 8)) {
-                    tmem_st_32cols(a_buf, hi);
-                    tmem_st_32cols(a_buf + 32, lo);
-                    tmem_st_wait();
-                }
-                tc_fence_before_sync();
-            } else {
-                // in place: raw -> hi (same spot), lo (A_lo tile); the pieces this lane staged itself
-#pragma unroll
-                for (int i = 0; i < PPT; ++i) {
-                    float4 *ph = reinterpret_cast<float4 *>(base + swz(rsub + 4 * i, q));
-                    float4 *pl = reinterpret_cast<float4 *>(base + OPERAND_BYTES + swz(rsub + 4 * i, q));
-                    const float4 v = *ph;
-                    float4 hi, lo;
-                    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                    if (!(dbg & 8)) { *ph = hi; *pl = lo; }
-                }
-                fence_proxy_async_smem();
-            }
-            mbar_arrive(&full[slot]);
-            tr.mark(6);
-            ++c_proc;
-            if (load_valid) issue();
-            cp_async_commit();
-            ++cp.kc;
-            if (cp.kc * CHUNK_K >= sg_proc.K) {
-                proc_valid = advance_seg(cp, t_proc);
-                if (proc_valid) sg_proc = Policy::segment(p, t_proc, cp.seg);
             }
         }
-        cp_async_wait<0>();
+        if (pending) {
+            tmem_st_wait();
+            tc_fence_before_sync();
+            mbar_arrive(&full[pending_slot]);
+        }
     } else if (warp < FIRST_EPI_WARP) {
-        // =========================================== MMA ISSUER (warp 4; warps 5-7 only give their registers away) ========
         reg_dealloc<MMA_REGS>();
         if (warp == MMA_WARP) {
+            // =========================================== MMA ISSUER ===========================================
             // The whole warp walks the loop converged (every lane polls the barriers) and one elected lane issues: the
             // descriptors then live in uniform registers.  Issued from an `if (lane == 0)` region every tcgen05.mma was
             // wrapped in an ELECT / R2UR.BROADCAST waterfall loop, ~100 cycles per instruction.
             const bool leader = elect_one();
             uint32_t c = 0, tcount = 0;
-            Tracer tr{(trace_base && leader) ? trace_base + 2048 : nullptr, 0};
+            Tracer tr{(trace_base && leader) ? trace_base + 2048 : nullptr, 0, 2048};
             typename Policy::Tile t;
             Policy::tile_init(t);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 tr.mark(10);
                 Policy::tile_setup(p, tile, t);
-                const uint32_t acc = tcount % M::NUM_ACC, acc_use = tcount / M::NUM_ACC;
-                tr.mark(11);
-                mbar_wait(&tmem_empty[acc], (acc_use & 1) ^ 1);   // the epilogue has drained this accumulator set
+                mbar_wait(tmem_empty, (tcount & 1) ^ 1);   // the epilogue has drained the accumulators
                 tr.mark(12);
                 tc_fence_after_sync();
-                const uint32_t tmem_acc = tmem_base + acc * 256;
                 const int nseg = Policy::num_segments(p, t);
                 for (int seg = 0; seg < nseg; ++seg) {
                     const Segment sg = Policy::segment(p, t, seg);
@@ -425,16 +335,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                         const uint32_t a_buf = tmem_base + A_TMEM_OFF + slot * 64;
                         const int kvalid = min(CHUNK_K, sg.K - kc * CHUNK_K);
                         const int ksteps = (dbg & 1) ? 0 : (kvalid + 7) / 8;
-                        // descriptors of K-step 0; later K-steps are +32 bytes (= +2 in the 16-byte address field) / +8 TMEM
-                        // columns, added as immediates in the unrolled loop (the issue rate of this one thread is the limit)
-                        const uint64_t sa_hi0 = make_smem_desc_sw128(base), sa_lo0 = make_smem_desc_sw128(base + OPERAND_BYTES);
+                        // descriptors of K-step 0; later K-steps are +32 bytes (= +2 in the 16-byte address field) / +8 TMEM columns
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi) {
                             if (gi < ng) {
-                                const uint64_t b_hi0 = make_smem_desc_sw128(base + M::B_HI_OFF + g[gi].row_off * 128);
-                                const uint64_t b_lo0 = make_smem_desc_sw128(base + M::B_LO_OFF + g[gi].row_off * 128);
+                                const uint64_t b_hi0 = make_smem_desc_sw128(base + B_HI_OFF + g[gi].row_off * 128);
+                                const uint64_t b_lo0 = make_smem_desc_sw128(base + B_LO_OFF + g[gi].row_off * 128);
                                 const uint32_t idesc_n = make_instr_desc(FMT_TF32, TILE_M, (uint32_t)g[gi].n);
-                                const uint32_t d_main = tmem_acc + g[gi].col_off, d_corr = d_main + CORR_OFF;
+                                const uint32_t d_main = tmem_base + g[gi].col_off, d_corr = d_main + CORR_OFF;
                                 const bool overwrite = g[gi].fresh && kc == 0;
                                 const uint32_t acc0 = overwrite ? 0u : 1u;
                                 const uint32_t idesc_first = (overwrite && g[gi].n_first > 0)
@@ -444,15 +352,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                                     if (ks < ksteps && leader) {
                                         const uint32_t first = ks == 0 ? acc0 : 1u;
                                         const uint32_t idesc = ks == 0 ? idesc_first : idesc_n;
-                                        if constexpr (TS) {
-                                            mma_tf32_ts(d_main, a_buf + ks * 8, b_hi0 + ks * 2, idesc, first);
-                                            mma_tf32_ts(d_corr, a_buf + ks * 8, b_lo0 + ks * 2, idesc, first);
-                                            mma_tf32_ts(d_corr, a_buf + 32 + ks * 8, b_hi0 + ks * 2, idesc, 1u);
-                                        } else {
-                                            mma_tf32_ss(d_main, sa_hi0 + ks * 2, b_hi0 + ks * 2, idesc, first);
-                                            mma_tf32_ss(d_corr, sa_hi0 + ks * 2, b_lo0 + ks * 2, idesc, first);
-                                            mma_tf32_ss(d_corr, sa_lo0 + ks * 2, b_hi0 + ks * 2, idesc, 1u);
-                                        }
+                                        // x * w ~= hi*hi (main) + hi*lo + lo*hi (correction accumulator)
+                                        mma_tf32_ts(d_main, a_buf + ks * 8, b_hi0 + ks * 2, idesc, first);
+                                        mma_tf32_ts(d_corr, a_buf + ks * 8, b_lo0 + ks * 2, idesc, first);
+                                        mma_tf32_ts(d_corr, a_buf + 32 + ks * 8, b_hi0 + ks * 2, idesc, 1u);
                                     }
                                 }
                             }
@@ -462,7 +365,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                         tr.mark(15);
                     }
                 }
-                if (leader) mma_commit(&tmem_full[acc]);
+                if (leader) mma_commit(tmem_full);
                 __syncwarp();
             }
         } else if (warp == TMA_WARP) {
@@ -490,12 +393,83 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                         if (!go && leader) mbar_arrive(&landed[slot]);
                         if (go && leader) mbar_expect_tx(&landed[slot], bytes);
                         if (go && sg.a_map != nullptr && leader) tma_load_2d(base, sg.a_map, kchunk, sg.a_row0, &landed[slot]);
-                        if (go && leader) tma_load_2d(base + M::B_HI_OFF, sg.b_hi_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
-                        if (go && leader) tma_load_2d(base + M::B_LO_OFF, sg.b_lo_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+                        if (go && leader) tma_load_2d(base + B_HI_OFF, sg.b_hi_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
+                        if (go && leader) tma_load_2d(base + B_LO_OFF, sg.b_lo_map, sg.b_col0 + kchunk, sg.b_row0, &landed[slot]);
                         __syncwarp();
                     }
                 }
             }
+        } else if (Policy::GATHER) {
+            // =========================================== ROW GATHERERS (warps 6-7) ===========================================
+            // 64 threads stage the gathered A rows of every chunk with 16-byte cp.async (LDGSTS, no registers): thread g
+            // copies piece q = g & 7 of rows (g >> 3) + 8 i, i < 16.  Completion is signalled on landed[slot] by
+            // cp.async.mbarrier.arrive, so nobody waits on cp.async groups.  The row indices of a (tile, segment) sit in
+            // shared memory (two buffers); those of the next one are fetched from global memory one step ahead.
+            const int g = (int)threadIdx.x - FIRST_GATHER_WARP * 32;
+            const int q = g & 7, rsub = g >> 3;
+            Tracer tr{(trace_base && g == 0) ? trace_base + 1024 : nullptr, 0, 1024};
+            uint32_t c = 0;
+            int buf = 0;
+            typename Policy::Tile t, t_next;
+            Policy::tile_init(t);
+            int tile = blockIdx.x, seg = 0;
+            bool valid = tile < total_tiles;
+            int v0 = -1, v1 = -1;
+            if (valid) {
+                Policy::tile_setup(p, tile, t);
+                v0 = Policy::gather_row(p, t, 0, g);
+                v1 = Policy::gather_row(p, t, 0, g + 64);
+            }
+            while (valid) {
+                int32_t *rows_s = index_buf + buf * TILE_M;
+                rows_s[g] = v0;
+                rows_s[g + 64] = v1;
+                named_bar_sync(1, GATHER_THREADS);
+                // the (tile, segment) after this one
+                int tile_n = tile, seg_n = seg + 1;
+                t_next = t;
+                bool valid_n = true;
+                if (seg_n >= Policy::num_segments(p, t)) {
+                    seg_n = 0;
+                    tile_n = tile + gridDim.x;
+                    valid_n = tile_n < total_tiles;
+                    if (valid_n) Policy::tile_setup(p, tile_n, t_next);
+                }
+                if (valid_n) {
+                    v0 = Policy::gather_row(p, t_next, seg_n, g);
+                    v1 = Policy::gather_row(p, t_next, seg_n, g + 64);
+                }
+                const Segment sg = Policy::segment(p, t, seg);
+                const int nkc = (sg.K + CHUNK_K - 1) / CHUNK_K;
+                // this thread's 16 rows of the (tile, segment): indices -> registers once, so that the per-chunk loop is just
+                // address arithmetic + LDGSTS (64 threads must sustain the SM's ~53 GB/s LDGSTS rate)
+                int rows[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rows[i] = rows_s[rsub + 8 * i];
+                const float *a_q = sg.a + q * 4;
+                const uint32_t soff = swz(rsub, q);     // rows rsub + 8 i share (row & 7): the swizzle term is per-thread constant
+                for (int kc = 0; kc < nkc; ++kc, ++c) {
+                    const uint32_t slot = c % NUM_SLOTS, use = c / NUM_SLOTS;
+                    tr.mark(1);
+                    mbar_wait(&a_free[slot], (use & 1) ^ 1);
+                    tr.mark(2);
+                    const int kchunk = kc * CHUNK_K;
+                    const bool k_ok = kchunk + q * 4 < sg.K;
+                    const uint32_t sbase = smem_u32(ring + slot * SLOT_BYTES) + soff;
+                    if (!(dbg & 2)) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const bool ok = k_ok && rows[i] >= 0;
+                            const float *src = ok ? a_q + (size_t)rows[i] * sg.lda + kchunk : sg.a;
+                            cp_async16(sbase + i * 1024, src, ok ? 16 : 0);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&landed[slot]);
+                }
+                tile = tile_n; seg = seg_n; t = t_next; valid = valid_n;
+                buf ^= 1;
+            }
+            cp_async_wait<0>();
         }
     } else {
         // =========================================== EPILOGUE ===========================================
@@ -506,10 +480,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float *stage = stage_base + ew * (STAGE_BYTES_PER_WARP / 4);
         uint32_t tcount = 0;
-        Tracer tr{(trace_base && ew == 0 && lane == 0) ? trace_base + 4096 : nullptr, 0};
+        Tracer tr{(trace_base && ew == 0 && lane == 0) ? trace_base + 4096 : nullptr, 0, 2048};
         typename Policy::Tile t, t_next;
         // What the store needs from global memory (destination offsets, the GRU's h values) is fetched one tile ahead: the
-        // epilogue is a serial per-tile chain and a load issued at store time queues behind the producers' gathers.
+        // epilogue is a serial per-tile chain and a load issued at store time queues behind the gathers.
         typename Policy::Pre pre, pre_next;
         int tile = blockIdx.x;
         Policy::tile_init(t);
@@ -524,16 +498,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_kernel(const __gri
                 Policy::tile_setup(p, next, t_next);
                 Policy::prefetch(p, t_next, quarter, half, lane, pre_next);
             }
-            const uint32_t aset = tcount % M::NUM_ACC, aset_use = tcount / M::NUM_ACC;
             tr.mark(20);
-            mbar_wait_warp(&tmem_full[aset], aset_use & 1, lane);
+            mbar_wait(tmem_full, tcount & 1);
             tr.mark(21);
             tc_fence_after_sync();
             float acc[64];
-            Policy::drain(p, t, tmem_lane + aset * 256, half, acc);
+            Policy::drain(p, t, tmem_lane, half, acc);
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[aset]);   // this accumulator set may be overwritten while we store
+            if (lane == 0) mbar_arrive(tmem_empty);   // the accumulators may be overwritten while we store
             tr.mark(22);
             if (!(dbg & 4)) Policy::store(p, t, acc, pre, half, lane, stage);
             tr.mark(23);

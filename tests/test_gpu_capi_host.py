@@ -73,9 +73,3 @@ def test_host_entry_point_reports_bad_indices():
     assert rc == -5 and b"outside" in N.lib().ptgnn_b200_last_error()
 
 
-def test_layers_with_ss_operand_staging():
-    """PTGNN_TC_MODE=ss: A split in shared memory, double-buffered accumulators (kept as an A/B alternative)."""
-    env = dict(os.environ, PTGNN_TC_MODE="ss")
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_layers.py", "-q", "-m", "gpu", "-x"], cwd=ROOT, env=env,
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 lib = ctypes.CDLL(N.LIB_PATH)
 buf = np.zeros(3 * 2048, dtype=np.uint64)
 assert lib.ptgnn_b200_debug_trace(buf.ctypes.data_as(ctypes.c_void_p)) == 1
-names = {1: "P issue:enter", 2: "P issue:empty ok", 3: "P proc:enter", 4: "P cp.async ok", 5: "P landed ok", 6: "P full arrived",
+names = {1: "G wait empty", 2: "G empty ok", 3: "P wait landed", 4: "P cp.async ok", 5: "P landed ok", 6: "P full arrived(prev)",
          10: "M tile", 11: "M setup done", 12: "M tmem_empty ok", 13: "M wait full", 14: "M full ok", 16: "M landed ok", 15: "M committed",
          20: "E wait tmem_full", 21: "E tmem_full ok", 22: "E drained+released", 23: "E stored"}
 ev = []
