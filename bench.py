@@ -51,7 +51,7 @@ def measured_tensor_peak():
 
 # DRAM traffic per launch (read + write bytes) of the kernels from the committed ncu --set full capture
 # (profiles/r01_final_*.md); None when no capture of the current kernel exists.
-NCU_TRAFFIC = {"message": 943.8e6, "reduce": 620.6e6, "gru": 289.3e6}   # profiles/r01_final_kernels.md (config 2, sum)
+NCU_TRAFFIC = {"message": 945.1e6, "reduce": 621.0e6, "gru": 290.2e6}   # profiles/r01b_kernels_f32.md (config 2, sum)
 
 
 def usable_cores() -> int:
@@ -457,16 +457,38 @@ def main():
                 entry["alg_tflops"] = alg_flops[name] / (avg_ms * 1e-3) / 1e12
                 entry["frac_tensor_bf16_peak"] = entry["alg_tflops"] / tensor_peak
             kernels[name] = entry
-    # the kernel with the largest share of the step; every kernel of this path has HBM as its higher floor
+    # Which roofline bounds a kernel: the larger of its HBM floor (algorithmic bytes / measured copy bandwidth) and its tensor
+    # floor.  fp32 results on the tensor cores need 3xTF32 (three kind::tf32 MMAs per product, tf32 dense rate = half the
+    # measured bf16 rate), so the fp32-exact ceiling in ALGORITHMIC flops is tensor_peak / 2 / 3; bf16 kernels use tensor_peak.
+    exact_peak = tensor_peak / 2.0 / 3.0 if args.dtype == "f32" else tensor_peak
+    for name, entry in kernels.items():
+        if "alg_bytes" not in entry:
+            continue
+        t_hbm = entry["alg_bytes"] / (peak * 1e9)
+        t_tensor = alg_flops[name] / (exact_peak * 1e12) if name in alg_flops else 0.0
+        entry["floor_ms"] = {"hbm": t_hbm * 1e3, "tensor": t_tensor * 1e3}
+        entry["bound"] = "tensor" if t_tensor > t_hbm else "hbm"
+        if name in alg_flops:
+            entry["frac_tensor_exact_peak"] = entry["alg_tflops"] / exact_peak
+    # the kernel with the largest share of the step
     dominant = max((k for k in kernels if k in alg_bytes), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
-    roofline = {
-        "kernel": kernels[dominant]["kernel"], "bound": "hbm", "achieved": kernels[dominant]["achieved_gbs"], "peak": peak,
-        "unit": "GB/s", "frac": kernels[dominant]["frac_hbm"],
-        "traffic": NCU_TRAFFIC.get(dominant) if args.dtype == "f32" else None, "peak_source": peak_src,
-        "note": "dominant kernel by time; its HBM floor exceeds its bf16-tensor floor, but it runs fp32-exact 3xTF32 MMAs "
-                "(3 tensor instructions per K=8 step), see kernels[*].alg_tflops; the HBM-bound kernel proper is "
-                "segment_reduce_stream_kernel (kernels.reduce.frac_hbm)",
-    }
+    dk = kernels[dominant]
+    if dk["bound"] == "tensor":
+        roofline = {
+            "kernel": dk["kernel"], "bound": "tensor", "achieved": dk["alg_tflops"], "peak": exact_peak, "unit": "TFLOP/s",
+            "frac": dk["alg_tflops"] / exact_peak, "traffic": NCU_TRAFFIC.get(dominant) if args.dtype == "f32" else None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 rate) / 3 (3xTF32 products per fp32 product)"
+                           if args.dtype == "f32" else "MEASURED_PEAKS.json bf16_tflops_sustained",
+            "note": "dominant kernel by time. achieved = the reference's fp32 multiply-adds (x2) per launch / launch time; the "
+                    "kernel issues 3 kind::tf32 MMAs per product to stay fp32-exact, so its tensor floor exceeds its HBM floor "
+                    "(kernels[*].floor_ms).  The HBM-bound kernel proper is the segmented reduce (kernels.reduce.frac_hbm).",
+        }
+    else:
+        roofline = {
+            "kernel": dk["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": dk["frac_hbm"], "traffic": NCU_TRAFFIC.get(dominant) if args.dtype == "f32" else None, "peak_source": peak_src,
+            "note": "dominant kernel by time; algorithmic bytes per launch / launch time (kernels[*].floor_ms has both floors)",
+        }
     b_min = 2 * n_nodes * HIDDEN * esz + 8 * E + (T * D * HIDDEN + 6 * HIDDEN * HIDDEN + 6 * HIDDEN) * esz
     layer_ms = ms_step / NUM_LAYERS
     layer_roofline = {"alg_bytes_fully_fused": b_min, "achieved_gbs": b_min / (layer_ms * 1e-3) / 1e9,
