@@ -107,7 +107,7 @@ struct MsgPolicy {
         const float *h, *h_tgt;           // rows indexed by src32 / by tgt32
         const int32_t *src32, *tgt32, *pos;
         float *msg;
-        int H, D, Kw, use_target, num_types, n_blocks, dbg;
+        int H, D, Kw, use_target, num_types, n_blocks, dbg, store_hint;
         unsigned long long *trace;
         int32_t edge_off[PTGNN_MAX_EDGE_TYPES + 1];
         int32_t tile_off[PTGNN_MAX_EDGE_TYPES + 1];
@@ -159,11 +159,12 @@ struct MsgPolicy {
     }
     __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage) {
         const long long row_off = pre.pos >= 0 ? (long long)pre.pos * p.D + ti.n0 : -1;
+        const uint64_t policy = p.store_hint ? l2_policy_evict_first() : 0;
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
             const int c0 = 64 * half + 32 * cb;
-            if (ti.b_rows - c0 >= 32) warp_store_rows<32>(stage, &acc[32 * cb], p.msg + c0, row_off, lane);
-            else if (ti.b_rows - c0 >= 16) warp_store_rows<16>(stage, &acc[32 * cb], p.msg + c0, row_off, lane);   // D % 32 == 16
+            if (ti.b_rows - c0 >= 32) warp_store_rows<32>(stage, &acc[32 * cb], p.msg + c0, row_off, lane, policy);
+            else if (ti.b_rows - c0 >= 16) warp_store_rows<16>(stage, &acc[32 * cb], p.msg + c0, row_off, lane, policy);   // D % 32 == 16
         }
     }
 };
@@ -321,7 +322,7 @@ static int sm_count() {
     return n;
 }
 
-int l2_hint_flags() {   // PTGNN_L2_HINTS bitmask (default 0; measured: no gain on B200): 4 = reduce loads with L2 evict-first
+int l2_hint_flags() {   // PTGNN_L2_HINTS bitmask (default 0): 1 = message stores, 4 = reduce loads with an L2 evict-first policy
     static int v = -1;
     if (v < 0) { const char *e = getenv("PTGNN_L2_HINTS"); v = e ? atoi(e) : 0; }
     return v;
@@ -393,6 +394,7 @@ int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_
     if (rc) return rc;
     p.h = h_src; p.h_tgt = h_tgt; p.src32 = src32; p.tgt32 = tgt32; p.pos = pos; p.msg = msg;
     p.H = H; p.D = D; p.Kw = Kw; p.use_target = use_target; p.num_types = num_types; p.n_blocks = (D + 127) / 128;
+    p.store_hint = (l2_hint_flags() & 1) ? 1 : 0;
     int tiles = 0;
     for (int t = 0; t < num_types; ++t) {
         p.edge_off[t] = (int32_t)type_off[t];

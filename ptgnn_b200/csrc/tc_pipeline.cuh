@@ -118,8 +118,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 // different 128-byte lines.  Staging 32 rows x NCOLS through a (chunk-XOR-swizzled) buffer lets each store
 // instruction write whole rows: 4 (NCOLS = 32) or 8 (NCOLS = 16) lines per instruction instead of 32.
 // `row_off` is this lane's destination element offset from `dst_base` (negative = row not stored).
+__device__ __forceinline__ void st_global_f4(float *dst, const float4 &v, uint64_t policy) {
+    if (policy == 0) { *reinterpret_cast<float4 *>(dst) = v; return; }
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+                 : "memory");
+}
+// `policy` != 0: an L2 cache policy (createpolicy) for the stores, e.g. evict-first for the message rows -- they are
+// written once and read once by the reduce, and must not push the gathered node states out of L2.
 template <int NCOLS>
-__device__ __forceinline__ void warp_store_rows(float *stage, const float *v, float *dst_base, long long row_off, int lane) {
+__device__ __forceinline__ void warp_store_rows(float *stage, const float *v, float *dst_base, long long row_off, int lane,
+                                                uint64_t policy = 0) {
     constexpr int CPR = NCOLS / 4;   // 16-byte chunks per row
 #pragma unroll
     for (int j = 0; j < CPR; ++j)
@@ -131,7 +139,7 @@ __device__ __forceinline__ void warp_store_rows(float *stage, const float *v, fl
         const int idx = it * 32 + lane, row = idx / CPR, ch = idx % CPR;
         const float4 val = *reinterpret_cast<const float4 *>(stage + (row * CPR + (ch ^ (row & (CPR - 1)))) * 4);
         const long long off = __shfl_sync(0xffffffffu, row_off, row);
-        if (off >= 0) *reinterpret_cast<float4 *>(dst_base + off + ch * 4) = val;
+        if (off >= 0) st_global_f4(dst_base + off + ch * 4, val, policy);
     }
     __syncwarp();
 }
