@@ -2,10 +2,10 @@
 // accumulate in TMEM), mbarrier pipelines, TMEM allocation and readback.  Hand-written inline PTX; no CUTLASS.
 //
 // fp32 accuracy on TF32 tensor cores ("3xTF32"): every fp32 operand x is split as x = hi + lo with
-// hi = x with the low 13 mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32,
-// <= 13 significant bits).  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi; the dropped a_lo*b_lo term and the TF32
-// truncation of the lo parts are both O(2^-22) relative, i.e. fp32-rounding level, which is what keeps the layer
-// inside the north_star's 1e-5 tolerance (a single TF32 product would be ~1e-3).
+// hi = x rounded to TF32 (low 13 mantissa bits zero) and lo = x - hi (exact in fp32, |lo| <= 2^-12 |x|).
+// a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi; the dropped a_lo*b_lo term (2^-24) and the TF32 truncation of the lo
+// parts (2^-23) are fp32-rounding level, which is what keeps the layer inside the north_star's 1e-5 tolerance (a single
+// TF32 product would be ~1e-3).
 //
 // Shared-memory operand layout (both A and B are K-major, rows of 32 fp32 = 128 bytes): the canonical
 // SWIZZLE_128B K-major layout -- 8-row groups of 1024 bytes, 16-byte chunk index XOR (row & 7).  One tcgen05.mma
@@ -217,7 +217,15 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 
 // ---- 3xTF32 operand split -----------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// x = hi + lo with hi a TF32 value (low 13 mantissa bits zero).  hi is x ROUNDED to TF32 (cvt.rna), not truncated:
+// |lo| <= 2^-12 |x| instead of 2^-11, which halves what the tensor core loses when it truncates lo to TF32 and quarters
+// the dropped lo*lo term (worst layer error in the config-5 sweep 8.1e-6 -> 6.7e-6).  Rounding overflows to inf only for
+// |x| within 2^-12 of FLT_MAX, where the products overflow anyway.
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r & 0xFFFFE000u);
+}
 
 }  // namespace tc
 }  // namespace ptgnn
