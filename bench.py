@@ -79,48 +79,97 @@ def usable_cores() -> int:
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region.  NVML (pynvml) polled every few ms from a thread -- the
+    timed region is only ~0.1 s, too short for `nvidia-smi -lms` -- with nvidia-smi as the fallback."""
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.samples = []
+        self.samples = []          # (sm_mhz, power_w, reasons bitmask or list)
+        self.sm_max = None
         self.proc = None
+        self.stop = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _poll_nvml(self, nv, h):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            try:
+                self.samples.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                     int(get_reasons(h))))
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def __enter__(self):
         try:
+            nv, h = self._nvml_handle()
+            self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.source = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 8:
-                self.samples.append(parts)
+                try:
+                    reasons = [n for n, c in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7))
+                               if parts[c].lower().startswith("active")]
+                    self.samples.append((int(float(parts[1])), float(parts[3]), reasons))
+                    self.sm_max = int(float(parts[2]))
+                except ValueError:
+                    pass
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(float(s[1])) for s in self.samples)
-        reasons = []
-        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
-            if any(s[col].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][2])), "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(float(s[3]) for s in self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = set()
+        for _, _, r in self.samples:
+            if isinstance(r, int):   # NVML bitmask (nvml.h nvmlClocksEventReason*)
+                for name, bit in (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+                    if r & bit:
+                        reasons.add(name)
+            else:
+                reasons.update(r)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(s[1] for s in self.samples), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------------
