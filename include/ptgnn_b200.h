@@ -160,6 +160,22 @@ int ptgnn_b200_mlp_forward_f32(const float *node_states, const float *gather_sta
                                const float *dense_bias, int32_t dense_activation, float *out_states, void *workspace,
                                size_t workspace_bytes, void *stream);
 
+/* bf16 variant: node_states / gather_states / out_states are bf16 (raw uint16 bits), every parameter stays fp32 and is
+ * converted per call; messages bf16, aggregation + activation + LayerNorm in fp32, dense update bf16 with fp32 accumulation
+ * (the reference under torch.autocast(bfloat16)).  Needs in_dim % 32 == 0 (>= 64), message_dim % 16 == 0 in [64, 256],
+ * out_dim % 16 == 0 (>= 64) when a dense layer is present. */
+size_t ptgnn_b200_mlp_workspace_bytes_bf16(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t in_dim,
+                                           int32_t message_dim, int32_t out_dim, int32_t use_target_state);
+int ptgnn_b200_mlp_forward_bf16(const uint16_t *node_states, const uint16_t *gather_states /* NULL: node_states */,
+                                int64_t num_nodes, int32_t in_dim, int32_t message_dim, int32_t out_dim, int32_t num_types,
+                                const int64_t *type_off /*[host]*/, const int32_t *row_ptr, const int32_t *pos,
+                                const int32_t *src32, const int32_t *tgt32,
+                                const float *const *edge_weights /*[host] T device pointers, fp32*/,
+                                int32_t use_target_state, int32_t reduce, int32_t message_activation,
+                                const float *ln_weight, const float *ln_bias, float ln_eps, const float *dense_weight,
+                                const float *dense_bias, int32_t dense_activation, uint16_t *out_states, void *workspace,
+                                size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry point (used for the end-to-end measurement): all pointers are HOST
  * memory; copies inputs to the device, builds the plan, runs `num_layers` GatedMessagePassingLayers

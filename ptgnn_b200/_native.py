@@ -39,6 +39,10 @@ SIGNATURES = {
     "ptgnn_b200_mlp_forward_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_f32, c_void_p, c_void_p, c_i32,
                                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptgnn_b200_mlp_workspace_bytes_bf16": (c_size_t, [c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    "ptgnn_b200_mlp_forward_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_f32, c_void_p, c_void_p, c_i32,
+                                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_gated_gnn_forward_host_f32": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32,
                                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p]),
 }

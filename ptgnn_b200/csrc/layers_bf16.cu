@@ -78,9 +78,10 @@ __global__ void pack_gru_bf16_kernel(const float *__restrict__ w_ih, const float
 // ---- policy: per-edge messages -------------------------------------------------------------------------------
 struct MsgPolicyB {
     struct Params {
-        CUtensorMap map_w;                 // [T*D, H] bf16, box {64, min(128, D)}
-        const __nv_bfloat16 *h;            // rows indexed by src32
-        const int32_t *src32, *pos;
+        CUtensorMap map_w;                 // [T*D, Kw] bf16 (Kw = H, or 2H with target states), box {64, min(128, D)}
+        const __nv_bfloat16 *h, *h_tgt;    // rows indexed by src32 / by tgt32 (Mlp layers with use_target_state)
+        const int32_t *src32, *tgt32, *pos;
+        int use_target;
         __nv_bfloat16 *msg;                // [E, D] bf16 at target-sorted rows
         unsigned long long *trace;
         int H, D, num_types, n_blocks, dbg;   // dbg: PTGNN_TC_DEBUG ablation bits (1 no MMA, 2 no store, 4 no loads, 8 no drain)
@@ -103,19 +104,20 @@ struct MsgPolicyB {
         ti.n0 = nb * 128;
         ti.b_rows = min(128, p.D - ti.n0);
     }
-    __device__ static int num_segments(const Params &, const Tile &) { return 1; }
-    __device__ static Segment segment(const Params &p, const Tile &ti, int) {
+    __device__ static int num_segments(const Params &p, const Tile &) { return p.use_target ? 2 : 1; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int seg) {
         Segment s;
-        s.a = p.h; s.lda = p.H; s.K = p.H; s.a_map = nullptr; s.a_row0 = 0;
-        s.b_map = &p.map_w; s.b_row0 = ti.t * p.D + ti.n0; s.b_col0 = 0; s.b_box_rows = min(128, p.D);
+        s.a = seg == 0 ? p.h : p.h_tgt; s.lda = p.H; s.K = p.H; s.a_map = nullptr; s.a_row0 = 0;
+        s.b_map = &p.map_w; s.b_row0 = ti.t * p.D + ti.n0; s.b_col0 = seg * p.H; s.b_box_rows = min(128, p.D);
         return s;
     }
-    __device__ static int gather_row(const Params &p, const Tile &ti, int, int r) {
+    __device__ static int gather_row(const Params &p, const Tile &ti, int seg, int r) {
         const int e = ti.e0 + r;
-        return e < ti.e_end ? p.src32[e] : -1;
+        if (e >= ti.e_end) return -1;
+        return seg == 0 ? p.src32[e] : p.tgt32[e];
     }
-    __device__ static int mma_groups(const Params &, const Tile &ti, int, MmaGroup (&g)[2]) {
-        g[0] = MmaGroup{ti.b_rows, 0, 0, true};
+    __device__ static int mma_groups(const Params &, const Tile &ti, int seg, MmaGroup (&g)[2]) {
+        g[0] = MmaGroup{ti.b_rows, 0, 0, seg == 0};
         return 1;
     }
     __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
@@ -225,13 +227,75 @@ struct GruPolicyB {
     }
 };
 
+// ---- policy: Mlp dense update  out = act(y W^T + b), bf16 in / out, fp32 accumulate -------------------------------
+struct DensePolicyB {
+    struct Params {
+        CUtensorMap map_y, map_w;          // [N, D] box {64, 128}; [Hout, D] box {64, min(128, Hout)}
+        const float *bias;                 // fp32 [Hout] or nullptr
+        __nv_bfloat16 *out;                // [N, Hout]
+        unsigned long long *trace;
+        int num_nodes, D, Hout, act, n_blocks, dbg;
+    };
+    struct Tile { int row0, n0, b_rows; };
+    __device__ static int num_tiles(const Params &p) { return ((p.num_nodes + TILE_M - 1) / TILE_M) * p.n_blocks; }
+    __device__ static void tile_init(Tile &) {}
+    __device__ static void tile_setup(const Params &p, int tile, Tile &ti) {
+        const int rb = tile / p.n_blocks;
+        ti.row0 = rb * TILE_M;
+        ti.n0 = (tile - rb * p.n_blocks) * 128;
+        ti.b_rows = min(128, p.Hout - ti.n0);
+    }
+    __device__ static int num_segments(const Params &, const Tile &) { return 1; }
+    __device__ static Segment segment(const Params &p, const Tile &ti, int) {
+        Segment s;
+        s.a = nullptr; s.lda = 0; s.a_map = &p.map_y; s.a_row0 = ti.row0; s.K = p.D;
+        s.b_map = &p.map_w; s.b_row0 = ti.n0; s.b_col0 = 0; s.b_box_rows = min(128, p.Hout);
+        return s;
+    }
+    __device__ static int gather_row(const Params &, const Tile &, int, int) { return -1; }
+    __device__ static int mma_groups(const Params &, const Tile &ti, int, MmaGroup (&g)[2]) {
+        g[0] = MmaGroup{ti.b_rows, 0, 0, true};
+        return 1;
+    }
+    __device__ static void drain(const Params &, const Tile &ti, uint32_t tmem_lane, int half, float (&acc)[64]) {
+        drain_2x32(tmem_lane, 64 * half, ti.b_rows, acc);
+    }
+    struct Pre { long long row_off; };     // 4-byte words of the bf16 output (no global load needed)
+    __device__ static void prefetch(const Params &p, const Tile &ti, int quarter, int, int lane, Pre &pre) {
+        const int row = ti.row0 + quarter * 32 + lane;
+        pre.row_off = row < p.num_nodes ? ((long long)row * p.Hout + ti.n0) / 2 : -1;
+    }
+    __device__ static void smem_init(const Params &, float *) {}
+    __device__ static void store(const Params &p, const Tile &ti, float (&acc)[64], const Pre &pre, int half, int lane, float *stage, float *) {
+        const int c0 = 64 * half;
+        if (c0 >= ti.b_rows) return;
+        float w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float v0 = acc[2 * i], v1 = acc[2 * i + 1];
+            if (c0 + 2 * i < ti.b_rows) {      // pairs never straddle b_rows (Hout % 16 == 0)
+                if (p.bias) { v0 += p.bias[ti.n0 + c0 + 2 * i]; v1 += p.bias[ti.n0 + c0 + 2 * i + 1]; }
+                v0 = apply_act(v0, p.act); v1 = apply_act(v1, p.act);
+            }
+            w[i] = pack_bf16x2(v0, v1);
+        }
+        float *dst = reinterpret_cast<float *>(p.out) + c0 / 2;
+        if (ti.b_rows - c0 >= 64) tc::warp_store_rows<32>(stage, w, dst, pre.row_off, lane);
+        else if (ti.b_rows - c0 >= 32) tc::warp_store_rows<16>(stage, w, dst, pre.row_off, lane);
+        else tc::warp_store_rows<8>(stage, w, dst, pre.row_off, lane);   // 16 columns
+    }
+};
+
 // ---- segmented reduce over bf16 message rows (fp32 accumulation, bf16 result) ------------------------------------
 // Same flat streaming walk as segment_reduce_stream_kernel (reduce.cuh); a lane owns 4 consecutive bf16 columns
 // (8-byte loads), CHUNKS x 128 columns per row.
-template <int RED, int CHUNKS>
+// WITH_EPI (Mlp layers): activation + LayerNorm of the aggregated row in fp32 before the single rounding to bf16
+// (mlpmessagepassing.py:114-116; the same epilogue as segment_reduce_stream_kernel).
+struct ReduceEpilogueB { int act; const float *ln_w, *ln_b; float ln_eps; };
+template <int RED, int CHUNKS, bool WITH_EPI>
 __global__ void __launch_bounds__(256)
 segment_reduce_bf16_kernel(const __nv_bfloat16 *__restrict__ msg, const int32_t *__restrict__ row_ptr, int num_nodes, int D,
-                           __nv_bfloat16 *__restrict__ out) {
+                           __nv_bfloat16 *__restrict__ out, const ReduceEpilogueB epi) {
     constexpr int ROWS_PER_WARP = 16;
     constexpr int UNROLL = CHUNKS == 1 ? 8 : 4;
     const int lane = threadIdx.x & 31;
@@ -258,6 +322,40 @@ segment_reduce_bf16_kernel(const __nv_bfloat16 *__restrict__ msg, const int32_t 
             if (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN) {
                 if (a.x == init) a.x = 0.f; if (a.y == init) a.y = 0.f; if (a.z == init) a.z = 0.f; if (a.w == init) a.w = 0.f;
             }
+            if (WITH_EPI) { a.x = apply_act(a.x, epi.act); a.y = apply_act(a.y, epi.act); a.z = apply_act(a.z, epi.act); a.w = apply_act(a.w, epi.act); }
+            acc[c] = a;
+        }
+        if (WITH_EPI && epi.ln_w != nullptr) {
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c)
+                if (col_ok[c]) s += (acc[c].x + acc[c].y) + (acc[c].z + acc[c].w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s / (float)D;
+            float q = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c)
+                if (col_ok[c]) {
+                    const float dx = acc[c].x - mean, dy = acc[c].y - mean, dz = acc[c].z - mean, dw = acc[c].w - mean;
+                    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(q / (float)D + epi.ln_eps);
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c)
+                if (col_ok[c]) {
+                    const int col = (c * 32 + lane) * 4;
+                    const float4 w = *reinterpret_cast<const float4 *>(epi.ln_w + col);
+                    const float4 b = *reinterpret_cast<const float4 *>(epi.ln_b + col);
+                    acc[c].x = (acc[c].x - mean) * rstd * w.x + b.x; acc[c].y = (acc[c].y - mean) * rstd * w.y + b.y;
+                    acc[c].z = (acc[c].z - mean) * rstd * w.z + b.z; acc[c].w = (acc[c].w - mean) * rstd * w.w + b.w;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const float4 a = acc[c];
             if (col_ok[c]) {
                 uint2 o;
                 o.x = __float_as_uint(pack_bf16x2(a.x, a.y));
@@ -309,15 +407,31 @@ segment_reduce_bf16_kernel(const __nv_bfloat16 *__restrict__ msg, const int32_t 
 }
 
 template <int RED>
-static int launch_reduce_bf16(const __nv_bfloat16 *msg, const int32_t *row_ptr, int64_t N, int D, __nv_bfloat16 *out, cudaStream_t st) {
+static int launch_reduce_bf16(const __nv_bfloat16 *msg, const int32_t *row_ptr, int64_t N, int D, __nv_bfloat16 *out,
+                              const ReduceEpilogueB *epi, cudaStream_t st) {
     const unsigned grid = (unsigned)ceil_div(N, 8 * 16);
+    const ReduceEpilogueB e = epi ? *epi : ReduceEpilogueB{PTGNN_ACT_NONE, nullptr, nullptr, 0.0f};
     {
         TimedScope timed__(PTGNN_KERNEL_REDUCE, st);
-        if (D <= 128) segment_reduce_bf16_kernel<RED, 1><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out);
-        else segment_reduce_bf16_kernel<RED, 2><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out);
+        if (epi) {
+            if (D <= 128) segment_reduce_bf16_kernel<RED, 1, true><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out, e);
+            else segment_reduce_bf16_kernel<RED, 2, true><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out, e);
+        } else {
+            if (D <= 128) segment_reduce_bf16_kernel<RED, 1, false><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out, e);
+            else segment_reduce_bf16_kernel<RED, 2, false><<<grid, 256, 0, st>>>(msg, row_ptr, (int)N, D, out, e);
+        }
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
+}
+static int reduce_bf16(int reduce, const __nv_bfloat16 *msg, const int32_t *row_ptr, int64_t N, int D, __nv_bfloat16 *out,
+                       const ReduceEpilogueB *epi, cudaStream_t st) {
+    switch (reduce) {
+        case PTGNN_REDUCE_SUM: return launch_reduce_bf16<PTGNN_REDUCE_SUM>(msg, row_ptr, N, D, out, epi, st);
+        case PTGNN_REDUCE_MEAN: return launch_reduce_bf16<PTGNN_REDUCE_MEAN>(msg, row_ptr, N, D, out, epi, st);
+        case PTGNN_REDUCE_MAX: return launch_reduce_bf16<PTGNN_REDUCE_MAX>(msg, row_ptr, N, D, out, epi, st);
+        default: return launch_reduce_bf16<PTGNN_REDUCE_MIN>(msg, row_ptr, N, D, out, epi, st);
+    }
 }
 
 static int debug_bits() {
@@ -432,7 +546,8 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     MsgPolicyB::Params mp{};
     int rc = make_map_bf16(&mp.map_w, wb, (uint64_t)num_types * D, H, D < 128 ? D : 128);
     if (rc) return rc;
-    mp.h = hsrc; mp.src32 = src32; mp.pos = pos; mp.msg = msg; mp.H = H; mp.D = D; mp.num_types = num_types;
+    mp.h = hsrc; mp.h_tgt = h; mp.src32 = src32; mp.tgt32 = nullptr; mp.use_target = 0; mp.pos = pos; mp.msg = msg; mp.H = H; mp.D = D;
+    mp.num_types = num_types;
     mp.n_blocks = (D + 127) / 128;
     mp.dbg = debug_bits(); mp.trace = tc::trace_buffer(PTGNN_KERNEL_MESSAGE + 10);
     int tiles = 0;
@@ -446,12 +561,7 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     if (rc) return rc;
 
     // 2. segmented reduce (fp32 accumulate, bf16 result)
-    switch (reduce) {
-        case PTGNN_REDUCE_SUM: rc = launch_reduce_bf16<PTGNN_REDUCE_SUM>(msg, row_ptr, num_nodes, D, agg, st); break;
-        case PTGNN_REDUCE_MEAN: rc = launch_reduce_bf16<PTGNN_REDUCE_MEAN>(msg, row_ptr, num_nodes, D, agg, st); break;
-        case PTGNN_REDUCE_MAX: rc = launch_reduce_bf16<PTGNN_REDUCE_MAX>(msg, row_ptr, num_nodes, D, agg, st); break;
-        default: rc = launch_reduce_bf16<PTGNN_REDUCE_MIN>(msg, row_ptr, num_nodes, D, agg, st); break;
-    }
+    rc = reduce_bf16(reduce, msg, row_ptr, num_nodes, D, agg, nullptr, st);
     if (rc) return rc;
 
     // 3. GRUCell
@@ -465,4 +575,127 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     gp.h = h; gp.bias4 = bias4; gp.out = reinterpret_cast<__nv_bfloat16 *>(out_states);
     gp.num_nodes = (int)num_nodes; gp.H = H; gp.D = D; gp.n_jb = H / 32; gp.dbg = debug_bits(); gp.trace = tc::trace_buffer(PTGNN_KERNEL_GRU + 10);
     return launch_pipeline<GruPolicyB>(gp, (int)ceil_div(num_nodes, TILE_M) * gp.n_jb, PTGNN_KERNEL_GRU, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MlpMessagePassingLayer with bf16 states (mlpmessagepassing.py:68-117 under torch.autocast(bfloat16)): bf16 messages,
+// fp32 aggregation + GELU + LayerNorm, bf16 dense update with fp32 accumulation.  Parameters arrive in fp32.
+// ---------------------------------------------------------------------------------------------------------------
+namespace ptgnn {
+namespace tcb {
+struct MlpWsB { size_t msg, y, w, wd, total; };
+static MlpWsB mlp_ws_layout(int64_t N, int64_t E, int T, int H, int D, int Hout, int use_target) {
+    MlpWsB w{};
+    size_t o = 0;
+    auto add = [&](size_t cnt) { size_t at = o; o += ws_slice(cnt, 2); return at; };
+    w.msg = add((size_t)E * D + 8);
+    w.y = add((size_t)N * D + 8);
+    w.w = add((size_t)T * D * H * (use_target ? 2 : 1) + 8);
+    w.wd = add((size_t)Hout * D + 8);
+    w.total = o;
+    return w;
+}
+}  // namespace tcb
+}  // namespace ptgnn
+
+extern "C" size_t ptgnn_b200_mlp_workspace_bytes_bf16(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t in_dim,
+                                                      int32_t message_dim, int32_t out_dim, int32_t use_target_state) {
+    if (num_nodes < 0 || num_edges < 0 || num_types < 0 || in_dim <= 0 || message_dim <= 0 || out_dim <= 0) return 0;
+    return mlp_ws_layout(num_nodes, num_edges, num_types, in_dim, message_dim, out_dim, use_target_state).total;
+}
+
+extern "C" int ptgnn_b200_mlp_forward_bf16(const uint16_t *node_states, const uint16_t *gather_states, int64_t num_nodes,
+                                           int32_t in_dim, int32_t message_dim, int32_t out_dim, int32_t num_types,
+                                           const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
+                                           const int32_t *src32, const int32_t *tgt32, const float *const *edge_weights,
+                                           int32_t use_target_state, int32_t reduce, int32_t message_activation,
+                                           const float *ln_weight, const float *ln_bias, float ln_eps,
+                                           const float *dense_weight, const float *dense_bias, int32_t dense_activation,
+                                           uint16_t *out_states, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int H = in_dim, D = message_dim, ut = use_target_state ? 1 : 0, Kw = H * (1 + ut);
+    PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && type_off, "mlp_forward_bf16: bad num_types=%d", num_types);
+    const int64_t E = type_off[num_types];
+    PTGNN_CHECK_ARG(num_nodes >= 0 && num_nodes < INT32_MAX && E >= 0 && E < INT32_MAX, "mlp_forward_bf16: sizes out of range");
+    PTGNN_CHECK_ARG(dense_weight ? out_dim > 0 : out_dim == D, "mlp_forward_bf16: out_dim=%d inconsistent", out_dim);
+    if (H % 32 != 0 || D % 16 != 0 || H < 64 || D < 64 || D > 256 || H > 1024 || (dense_weight && (out_dim % 16 != 0 || out_dim < 64))) {
+        set_error("mlp_forward_bf16: needs state dim %% 32 == 0 (>= 64), message dim %% 16 == 0 in [64, 256], output dim %% 16 == 0 (>= 64); "
+                  "got %d, %d, %d", H, D, out_dim);
+        return PTGNN_E_UNSUPPORTED;
+    }
+    PTGNN_CHECK_ARG(reduce >= PTGNN_REDUCE_SUM && reduce <= PTGNN_REDUCE_MIN, "mlp_forward_bf16: bad reduce %d", reduce);
+    PTGNN_CHECK_ARG(message_activation >= PTGNN_ACT_NONE && message_activation <= PTGNN_ACT_RELU &&
+                        dense_activation >= PTGNN_ACT_NONE && dense_activation <= PTGNN_ACT_RELU, "mlp_forward_bf16: bad activation");
+    PTGNN_CHECK_ARG((ln_weight == nullptr) == (ln_bias == nullptr), "mlp_forward_bf16: ln_weight/ln_bias must both be set");
+    if (num_nodes == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(node_states && out_states && row_ptr, "mlp_forward_bf16: null pointer");
+    PTGNN_CHECK_ARG(E == 0 || (pos && src32 && edge_weights && (!ut || tgt32)), "mlp_forward_bf16: null edge arrays");
+    const MlpWsB L = mlp_ws_layout(num_nodes, E, num_types, H, D, out_dim, ut);
+    if (workspace_bytes < L.total || !workspace) {
+        set_error("mlp_forward_bf16: workspace %zu < required %zu", workspace_bytes, L.total);
+        return PTGNN_E_WORKSPACE;
+    }
+    char *ws = static_cast<char *>(workspace);
+    auto b16 = [&](size_t off) { return reinterpret_cast<__nv_bfloat16 *>(ws + off); };
+    const __nv_bfloat16 *h = reinterpret_cast<const __nv_bfloat16 *>(node_states);
+    const __nv_bfloat16 *hsrc = gather_states ? reinterpret_cast<const __nv_bfloat16 *>(gather_states) : h;
+    __nv_bfloat16 *out = reinterpret_cast<__nv_bfloat16 *>(out_states);
+    __nv_bfloat16 *msg = b16(L.msg), *wb = b16(L.w), *wd = b16(L.wd);
+    __nv_bfloat16 *y = dense_weight ? b16(L.y) : out;
+
+    // 0. weights -> bf16
+    int rc = PTGNN_OK;
+    if (num_types > 0) {
+        ConvSrc cs{};
+        cs.num = num_types; cs.elems = D * Kw;
+        for (int t = 0; t < num_types; ++t) cs.w[t] = edge_weights[t];
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            convert_weights_kernel<<<148, 256, 0, st>>>(cs, wb);
+        }
+        PTGNN_LAUNCHED();
+    }
+    if (dense_weight) {
+        ConvSrc cs{};
+        cs.num = 1; cs.elems = out_dim * D; cs.w[0] = dense_weight;
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            convert_weights_kernel<<<148, 256, 0, st>>>(cs, wd);
+        }
+        PTGNN_LAUNCHED();
+    }
+
+    // 1. messages  m_e = W_t [h_src ; h_tgt]
+    if (E > 0) {
+        MsgPolicyB::Params mp{};
+        rc = make_map_bf16(&mp.map_w, wb, (uint64_t)num_types * D, Kw, D < 128 ? D : 128);
+        if (rc) return rc;
+        mp.h = hsrc; mp.h_tgt = h; mp.src32 = src32; mp.tgt32 = tgt32; mp.use_target = ut; mp.pos = pos; mp.msg = msg; mp.H = H; mp.D = D;
+        mp.num_types = num_types;
+        mp.n_blocks = (D + 127) / 128;
+        mp.dbg = debug_bits(); mp.trace = tc::trace_buffer(PTGNN_KERNEL_MESSAGE + 10);
+        int tiles = 0;
+        for (int t = 0; t < num_types; ++t) {
+            mp.edge_off[t] = (int32_t)type_off[t];
+            mp.tile_off[t] = tiles;
+            tiles += (int)ceil_div(type_off[t + 1] - type_off[t], TILE_M);
+        }
+        for (int t = num_types; t <= PTGNN_MAX_EDGE_TYPES; ++t) { mp.edge_off[t] = (int32_t)type_off[num_types]; mp.tile_off[t] = tiles; }
+        rc = launch_pipeline<MsgPolicyB>(mp, tiles * mp.n_blocks, PTGNN_KERNEL_MESSAGE, st);
+        if (rc) return rc;
+    }
+
+    // 2. aggregate + activation + LayerNorm (fp32) -> y (bf16)
+    const ReduceEpilogueB epi{message_activation, ln_weight, ln_bias, ln_eps};
+    rc = reduce_bf16(reduce, msg, row_ptr, num_nodes, D, y, &epi, st);
+    if (rc || !dense_weight) return rc;
+
+    // 3. dense update
+    DensePolicyB::Params dp{};
+    rc = make_map_bf16(&dp.map_y, y, num_nodes, D, 128);
+    if (!rc) rc = make_map_bf16(&dp.map_w, wd, out_dim, D, out_dim < 128 ? out_dim : 128);
+    if (rc) return rc;
+    dp.bias = dense_bias; dp.out = out; dp.num_nodes = (int)num_nodes; dp.D = D; dp.Hout = out_dim; dp.act = dense_activation;
+    dp.n_blocks = (out_dim + 127) / 128; dp.dbg = debug_bits(); dp.trace = tc::trace_buffer(PTGNN_KERNEL_DENSE + 10);
+    return launch_pipeline<DensePolicyB>(dp, (int)ceil_div(num_nodes, TILE_M) * dp.n_blocks, PTGNN_KERNEL_DENSE, st);
 }

@@ -89,7 +89,7 @@ class AbstractMessagePassingLayer(nn.Module):
         `gather_states` the all-gathered states that the source ids index.  None in the ordinary single-GPU case."""
         if gather_states is None:
             return None
-        g = N.require_cuda(gather_states, "gather_states", torch.float32)
+        g = N.require_cuda(gather_states, "gather_states", h.dtype)
         if g.dim() != 2 or g.shape[1] != h.shape[1]:
             raise ValueError("gather_states must be [num_source_nodes, H]")
         return g
@@ -345,7 +345,8 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
             else:
                 dense_act = _activation_code(m, "dense_activation")
 
-        h = N.require_cuda(node_states, "node_states", torch.float32)
+        state_dtype = node_states.dtype if node_states.dtype == torch.bfloat16 else torch.float32
+        h = N.require_cuda(node_states, "node_states", state_dtype)
         num_nodes, H = h.shape
         D = self.__message_dim
         out_dim = dense.out_features if dense is not None else D
@@ -358,6 +359,20 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         d_b = f32(dense.bias, "dense.bias") if dense is not None and dense.bias is not None else None
 
         lib = N.lib()
+        if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
+            ut = int(self.__use_target_state_as_message_input)
+            ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes_bf16(num_nodes, plan.num_edges, plan.num_types, H, D, out_dim, ut)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
+            out = torch.empty(num_nodes, out_dim, dtype=torch.bfloat16, device=h.device)
+            with torch.cuda.device(h.device):
+                rc = lib.ptgnn_b200_mlp_forward_bf16(
+                    N.ptr(h), N.ptr(gsrc), num_nodes, H, D, out_dim, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
+                    N.ptr(plan.src32), N.ptr(plan.tgt32), N.ptr_table(weights), ut, reduce, msg_act, N.ptr(ln_w), N.ptr(ln_b),
+                    float(ln.eps) if ln is not None else 0.0, N.ptr(d_w), N.ptr(d_b), dense_act, N.ptr(out), N.ptr(ws), ws_bytes,
+                    N.current_stream(h.device),
+                )
+            N.check(rc, "ptgnn_b200_mlp_forward_bf16")
+            return out
         ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes(
             num_nodes, plan.num_edges, plan.num_types, H, D, out_dim, int(self.__use_target_state_as_message_input))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
