@@ -217,15 +217,13 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 
 // ---- 3xTF32 operand split -----------------------------------------------------------------------------------
-// x = hi + lo with hi a TF32 value (low 13 mantissa bits zero).  hi is x ROUNDED to TF32 (cvt.rna), not truncated:
-// |lo| <= 2^-12 |x| instead of 2^-11, which halves what the tensor core loses when it truncates lo to TF32 and quarters
-// the dropped lo*lo term (worst layer error in the config-5 sweep 8.1e-6 -> 6.7e-6).  Rounding overflows to inf only for
-// |x| within 2^-12 of FLT_MAX, where the products overflow anyway.
-__device__ __forceinline__ float tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r & 0xFFFFE000u);
-}
+// x = hi + lo with hi a TF32 value (low 13 mantissa bits zero).  hi is x ROUNDED to TF32 (nearest, ties away from zero --
+// what cvt.rna.tf32.f32 computes), not truncated: |lo| <= 2^-12 |x| instead of 2^-11, which halves what the tensor core
+// loses when it truncates lo to TF32 and quarters the dropped lo*lo term (worst layer error in the config-5 sweep
+// 8.1e-6 -> 6.7e-6).  Done on the bit pattern -- add half a TF32 ulp to the magnitude, clear the low 13 bits; a mantissa
+// carry correctly bumps the exponent -- because two full-rate integer ops beat the conversion pipe in the converters'
+// inner loop.  Rounding overflows to inf only for |x| within 2^-12 of FLT_MAX, where the products overflow anyway.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 }  // namespace tc
 }  // namespace ptgnn
