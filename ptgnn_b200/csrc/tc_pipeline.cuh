@@ -143,27 +143,6 @@ __device__ __forceinline__ void warp_store_rows(float *stage, const float *v, fl
     }
     __syncwarp();
 }
-// The mirror image for reads: every lane ends up with NCOLS consecutive floats of ITS row.
-template <int NCOLS>
-__device__ __forceinline__ void warp_load_rows(float *stage, float *v, const float *src_base, long long row_off, int lane) {
-    constexpr int CPR = NCOLS / 4;
-#pragma unroll
-    for (int it = 0; it < CPR; ++it) {
-        const int idx = it * 32 + lane, row = idx / CPR, ch = idx % CPR;
-        const long long off = __shfl_sync(0xffffffffu, row_off, row);
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (off >= 0) val = *reinterpret_cast<const float4 *>(src_base + off + ch * 4);
-        *reinterpret_cast<float4 *>(stage + (row * CPR + (ch ^ (row & (CPR - 1)))) * 4) = val;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < CPR; ++j) {
-        const float4 val = *reinterpret_cast<const float4 *>(stage + (lane * CPR + (j ^ (lane & (CPR - 1)))) * 4);
-        v[4 * j] = val.x; v[4 * j + 1] = val.y; v[4 * j + 2] = val.z; v[4 * j + 3] = val.w;
-    }
-    __syncwarp();
-}
-
 // accumulator value = main + correction; all TMEM loads of a drain are issued before ONE wait
 // drain 64 consecutive columns [c0, c0+64) (only the 32-column blocks below `ncols`); two loads in flight per wait
 __device__ __forceinline__ void tmem_drain_2x32(uint32_t taddr, int c0, int ncols, float (&acc)[64]) {
