@@ -128,6 +128,32 @@ int ptgnn_b200_gated_forward_f32(const float *node_states, const float *gather_s
                                  const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh, int32_t reduce,
                                  float *out_states, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Weight cache (optional).  Every forward call first derives working copies of the parameters (TF32 hi/lo splits,
+ * gate-blocked GRU packing; bf16 conversions in the bf16 variant).  A caller whose parameters do not change between calls
+ * (inference, or between optimiser steps) can own that buffer: pass `weight_cache` (device memory of at least
+ * `*_weight_cache_bytes`, 256-byte aligned) and `cache_valid` = 0 on the first call with a given set of parameter VALUES
+ * (the copies are derived into the cache), 1 afterwards (they are reused; the parameter pointers are then not read by the
+ * derivation).  `*_weight_cache_bytes` == 0 means these dimensions have nothing to cache: pass NULL.  Results are
+ * bit-identical to the uncached entry points. */
+size_t ptgnn_b200_gated_weight_cache_bytes(int32_t num_types, int32_t state_dim, int32_t message_dim);
+int ptgnn_b200_gated_forward_cached_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
+                                        int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                        const int64_t *type_off /*[host]*/, const int32_t *row_ptr, const int32_t *pos,
+                                        const int32_t *src32, const float *const *edge_weights /*[host]*/,
+                                        const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih,
+                                        const float *gru_b_hh, int32_t reduce, float *out_states, void *workspace,
+                                        size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                        int32_t cache_valid, void *stream);
+size_t ptgnn_b200_gated_weight_cache_bytes_bf16(int32_t num_types, int32_t state_dim, int32_t message_dim);
+int ptgnn_b200_gated_forward_cached_bf16(const uint16_t *node_states, const uint16_t *gather_states, int64_t num_nodes,
+                                         int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                         const int64_t *type_off /*[host]*/, const int32_t *row_ptr, const int32_t *pos,
+                                         const int32_t *src32, const float *const *edge_weights /*[host]*/,
+                                         const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih,
+                                         const float *gru_b_hh, int32_t reduce, uint16_t *out_states, void *workspace,
+                                         size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                         int32_t cache_valid, void *stream);
+
 /* bf16 variant (BASELINE.json configs[3]): node_states / gather_states / out_states are bf16 [*, H] (raw uint16 bits),
  * module parameters stay fp32 and are converted per call; messages and aggregates are bf16 in HBM, every accumulation
  * (tensor-core accumulators, segmented reduce, gate math) is fp32 -- the arithmetic of the reference under

@@ -35,6 +35,14 @@ SIGNATURES = {
     "ptgnn_b200_gated_workspace_bytes_bf16": (c_size_t, [c_i64, c_i64, c_i32, c_i32, c_i32]),
     "ptgnn_b200_gated_forward_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p,
                                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptgnn_b200_gated_weight_cache_bytes": (c_size_t, [c_i32, c_i32, c_i32]),
+    "ptgnn_b200_gated_forward_cached_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t,
+                                                           c_void_p, c_size_t, c_i32, c_void_p]),
+    "ptgnn_b200_gated_weight_cache_bytes_bf16": (c_size_t, [c_i32, c_i32, c_i32]),
+    "ptgnn_b200_gated_forward_cached_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t,
+                                                            c_void_p, c_size_t, c_i32, c_void_p]),
     "ptgnn_b200_mlp_workspace_bytes": (c_size_t, [c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "ptgnn_b200_mlp_forward_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_f32, c_void_p, c_void_p, c_i32,

@@ -317,14 +317,19 @@ extern "C" size_t ptgnn_b200_gated_workspace_bytes(int64_t num_nodes, int64_t nu
     return gated_ws_layout(num_nodes, num_edges, num_types, state_dim, message_dim).total;
 }
 
-extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
-                                            int32_t state_dim,
-                                            int32_t message_dim, int32_t num_types, const int64_t *type_off,
-                                            const int32_t *row_ptr, const int32_t *pos, const int32_t *src32,
-                                            const float *const *edge_weights, const float *gru_w_ih,
-                                            const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
-                                            int32_t reduce, float *out_states, void *workspace, size_t workspace_bytes,
-                                            void *stream) {
+// weight cache of the tensor-core path: [split edge weights | gate-blocked GRU weights + biases]; 0 when the dims run on
+// the FFMA kernels (nothing worth caching there)
+static size_t gated_cache_bytes(int T, int H, int D) {
+    if (!tc_enabled() || !tc::supported_message(H, D) || !tc::supported_gru(H, D)) return 0;
+    return tc::split_edge_weights_bytes(T, D, H) + tc::gru_pack_bytes(H, D);
+}
+
+static int gated_forward_impl(const float *node_states, const float *gather_states, int64_t num_nodes, int32_t state_dim,
+                              int32_t message_dim, int32_t num_types, const int64_t *type_off, const int32_t *row_ptr,
+                              const int32_t *pos, const int32_t *src32, const float *const *edge_weights,
+                              const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                              int32_t reduce, float *out_states, void *workspace, size_t workspace_bytes, void *weight_cache,
+                              size_t weight_cache_bytes, int32_t cache_valid, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int H = state_dim, D = message_dim;
     PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && type_off, "gated_forward: bad num_types=%d",
@@ -350,11 +355,24 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, const floa
     float *msg = reinterpret_cast<float *>(ws + L.msg), *agg = reinterpret_cast<float *>(ws + L.agg);
     float *P1 = reinterpret_cast<float *>(ws + L.p1), *P2 = reinterpret_cast<float *>(ws + L.p2);
     const float *gsrc = gather_states ? gather_states : node_states;   // rows that `src32` indexes (sharded runs)
+    // derived weights: in the workspace (re-derived every call) or in the caller's cache (derived when !cache_valid)
+    char *wsplit = ws + L.wsplit, *grupack = ws + L.grupack;
+    bool pack = true;
+    const size_t need_cache = gated_cache_bytes(num_types, H, D);
+    if (weight_cache != nullptr && need_cache > 0) {
+        if (weight_cache_bytes < need_cache) {
+            set_error("gated_forward: weight cache %zu < required %zu", weight_cache_bytes, need_cache);
+            return PTGNN_E_WORKSPACE;
+        }
+        wsplit = static_cast<char *>(weight_cache);
+        grupack = wsplit + tc::split_edge_weights_bytes(num_types, D, H);
+        pack = !cache_valid;
+    }
 
     // 1. per-edge messages, written at their target-sorted positions
     if (tc_enabled() && tc::supported_message(H, D)) {
         rc = tc::edge_messages(gsrc, node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg,
-                               ws + L.wsplit, st);
+                               wsplit, pack, st);
     } else {
         rc = launch_edge_messages(gsrc, node_states, H, D, 0, num_types, type_off, edge_weights, src32, nullptr, pos, msg,
                                   st);
@@ -366,7 +384,7 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, const floa
     // 3. GRUCell
     if (tc_enabled() && tc::supported_gru(H, D)) {
         return tc::gru_update(agg, node_states, num_nodes, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, out_states,
-                              ws + L.grupack, st);
+                              grupack, pack, st);
     }
     {
         TimedScope timed__(PTGNN_KERNEL_PACK, st);
@@ -384,6 +402,36 @@ extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, const floa
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
+}
+
+extern "C" int ptgnn_b200_gated_forward_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
+                                            int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                            const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
+                                            const int32_t *src32, const float *const *edge_weights, const float *gru_w_ih,
+                                            const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                                            int32_t reduce, float *out_states, void *workspace, size_t workspace_bytes,
+                                            void *stream) {
+    return gated_forward_impl(node_states, gather_states, num_nodes, state_dim, message_dim, num_types, type_off, row_ptr, pos,
+                              src32, edge_weights, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, reduce, out_states, workspace,
+                              workspace_bytes, nullptr, 0, 0, stream);
+}
+
+extern "C" size_t ptgnn_b200_gated_weight_cache_bytes(int32_t num_types, int32_t state_dim, int32_t message_dim) {
+    if (num_types < 0 || num_types > PTGNN_MAX_EDGE_TYPES || state_dim <= 0 || message_dim <= 0) return 0;
+    return gated_cache_bytes(num_types, state_dim, message_dim);
+}
+
+extern "C" int ptgnn_b200_gated_forward_cached_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
+                                                   int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                                   const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
+                                                   const int32_t *src32, const float *const *edge_weights,
+                                                   const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih,
+                                                   const float *gru_b_hh, int32_t reduce, float *out_states, void *workspace,
+                                                   size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                                   int32_t cache_valid, void *stream) {
+    return gated_forward_impl(node_states, gather_states, num_nodes, state_dim, message_dim, num_types, type_off, row_ptr, pos,
+                              src32, edge_weights, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, reduce, out_states, workspace,
+                              workspace_bytes, weight_cache, weight_cache_bytes, cache_valid, stream);
 }
 
 extern "C" size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t in_dim,
@@ -431,7 +479,7 @@ extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, const float 
 
     if (tc_enabled() && tc::supported_message(H, D)) {
         rc = tc::edge_messages(gsrc, node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg,
-                               ws + L.wsplit, st);
+                               ws + L.wsplit, true, st);
     } else {
         rc = launch_edge_messages(gsrc, node_states, H, D, ut, num_types, type_off, edge_weights, src32, tgt32, pos, msg,
                                   st);

@@ -490,13 +490,19 @@ extern "C" size_t ptgnn_b200_gated_workspace_bytes_bf16(int64_t num_nodes, int64
     return ws_layout(num_nodes, num_edges, num_types, state_dim, message_dim).total;
 }
 
-extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const uint16_t *gather_states, int64_t num_nodes,
-                                             int32_t state_dim, int32_t message_dim, int32_t num_types,
-                                             const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
-                                             const int32_t *src32, const float *const *edge_weights, const float *gru_w_ih,
-                                             const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
-                                             int32_t reduce, uint16_t *out_states, void *workspace, size_t workspace_bytes,
-                                             void *stream) {
+// weight cache of the bf16 path: the tail of the workspace layout [bf16 edge weights | P1 | P2 | bias4]
+static size_t gated_cache_bytes_bf16(int T, int H, int D) {
+    const WsB L = ws_layout(0, 0, T, H, D);
+    return L.total - L.w;
+}
+
+static int gated_forward_bf16_impl(const uint16_t *node_states, const uint16_t *gather_states, int64_t num_nodes,
+                                   int32_t state_dim, int32_t message_dim, int32_t num_types, const int64_t *type_off,
+                                   const int32_t *row_ptr, const int32_t *pos, const int32_t *src32,
+                                   const float *const *edge_weights, const float *gru_w_ih, const float *gru_w_hh,
+                                   const float *gru_b_ih, const float *gru_b_hh, int32_t reduce, uint16_t *out_states,
+                                   void *workspace, size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                   int32_t cache_valid, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int H = state_dim, D = message_dim;
     PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && type_off, "gated_forward_bf16: bad num_types=%d", num_types);
@@ -519,28 +525,44 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     auto b16 = [&](size_t off) { return reinterpret_cast<__nv_bfloat16 *>(ws + off); };
     const __nv_bfloat16 *h = reinterpret_cast<const __nv_bfloat16 *>(node_states);
     const __nv_bfloat16 *hsrc = gather_states ? reinterpret_cast<const __nv_bfloat16 *>(gather_states) : h;
-    __nv_bfloat16 *msg = b16(L.msg), *agg = b16(L.agg), *wb = b16(L.w), *p1 = b16(L.p1), *p2 = b16(L.p2);
+    __nv_bfloat16 *msg = b16(L.msg), *agg = b16(L.agg);
+    // derived weights live in the workspace (re-derived every call) or in the caller's cache (derived when !cache_valid)
+    char *wbase = ws + L.w;
+    bool pack = true;
+    if (weight_cache != nullptr) {
+        const size_t need = gated_cache_bytes_bf16(num_types, H, D);
+        if (weight_cache_bytes < need) {
+            set_error("gated_forward_bf16: weight cache %zu < required %zu", weight_cache_bytes, need);
+            return PTGNN_E_WORKSPACE;
+        }
+        wbase = static_cast<char *>(weight_cache);
+        pack = !cache_valid;
+    }
+    __nv_bfloat16 *wb = reinterpret_cast<__nv_bfloat16 *>(wbase);
+    __nv_bfloat16 *p1 = reinterpret_cast<__nv_bfloat16 *>(wbase + (L.p1 - L.w)), *p2 = reinterpret_cast<__nv_bfloat16 *>(wbase + (L.p2 - L.w));
+    float4 *bias4 = reinterpret_cast<float4 *>(wbase + (L.bias - L.w));
 
     // 0. weights -> bf16 (edge weights [T][D][H]; GRU gate blocks)
-    ConvSrc cs{};
-    cs.num = num_types; cs.elems = D * H;
-    for (int t = 0; t < num_types; ++t) cs.w[t] = edge_weights[t];
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        convert_weights_kernel<<<148, 256, 0, st>>>(cs, wb);
+    if (pack) {
+        ConvSrc cs{};
+        cs.num = num_types; cs.elems = D * H;
+        for (int t = 0; t < num_types; ++t) cs.w[t] = edge_weights[t];
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            convert_weights_kernel<<<148, 256, 0, st>>>(cs, wb);
+        }
+        PTGNN_LAUNCHED();
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            pack_gru_bf16_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, p1, p2);
+        }
+        PTGNN_LAUNCHED();
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            pack_gru_bias_bf16_kernel<<<(H + 127) / 128, 128, 0, st>>>(gru_b_ih, gru_b_hh, H, bias4);
+        }
+        PTGNN_LAUNCHED();
     }
-    PTGNN_LAUNCHED();
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        pack_gru_bf16_kernel<<<148, 256, 0, st>>>(gru_w_ih, gru_w_hh, H, D, p1, p2);
-    }
-    PTGNN_LAUNCHED();
-    float4 *bias4 = reinterpret_cast<float4 *>(ws + L.bias);
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        pack_gru_bias_bf16_kernel<<<(H + 127) / 128, 128, 0, st>>>(gru_b_ih, gru_b_hh, H, bias4);
-    }
-    PTGNN_LAUNCHED();
 
     // 1. messages
     MsgPolicyB::Params mp{};
@@ -575,6 +597,37 @@ extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const 
     gp.h = h; gp.bias4 = bias4; gp.out = reinterpret_cast<__nv_bfloat16 *>(out_states);
     gp.num_nodes = (int)num_nodes; gp.H = H; gp.D = D; gp.n_jb = H / 32; gp.dbg = debug_bits(); gp.trace = tc::trace_buffer(PTGNN_KERNEL_GRU + 10);
     return launch_pipeline<GruPolicyB>(gp, (int)ceil_div(num_nodes, TILE_M) * gp.n_jb, PTGNN_KERNEL_GRU, st);
+}
+
+extern "C" int ptgnn_b200_gated_forward_bf16(const uint16_t *node_states, const uint16_t *gather_states, int64_t num_nodes,
+                                             int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                             const int64_t *type_off, const int32_t *row_ptr, const int32_t *pos,
+                                             const int32_t *src32, const float *const *edge_weights, const float *gru_w_ih,
+                                             const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                                             int32_t reduce, uint16_t *out_states, void *workspace, size_t workspace_bytes,
+                                             void *stream) {
+    return gated_forward_bf16_impl(node_states, gather_states, num_nodes, state_dim, message_dim, num_types, type_off, row_ptr,
+                                   pos, src32, edge_weights, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, reduce, out_states,
+                                   workspace, workspace_bytes, nullptr, 0, 0, stream);
+}
+
+extern "C" size_t ptgnn_b200_gated_weight_cache_bytes_bf16(int32_t num_types, int32_t state_dim, int32_t message_dim) {
+    if (num_types < 0 || num_types > PTGNN_MAX_EDGE_TYPES || state_dim <= 0 || message_dim <= 0) return 0;
+    return gated_cache_bytes_bf16(num_types, state_dim, message_dim);
+}
+
+extern "C" int ptgnn_b200_gated_forward_cached_bf16(const uint16_t *node_states, const uint16_t *gather_states,
+                                                    int64_t num_nodes, int32_t state_dim, int32_t message_dim,
+                                                    int32_t num_types, const int64_t *type_off, const int32_t *row_ptr,
+                                                    const int32_t *pos, const int32_t *src32,
+                                                    const float *const *edge_weights, const float *gru_w_ih,
+                                                    const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                                                    int32_t reduce, uint16_t *out_states, void *workspace,
+                                                    size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                                    int32_t cache_valid, void *stream) {
+    return gated_forward_bf16_impl(node_states, gather_states, num_nodes, state_dim, message_dim, num_types, type_off, row_ptr,
+                                   pos, src32, edge_weights, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, reduce, out_states,
+                                   workspace, workspace_bytes, weight_cache, weight_cache_bytes, cache_valid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

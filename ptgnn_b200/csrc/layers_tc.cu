@@ -375,18 +375,20 @@ bool supported_dense(int D, int Hout) { return D % 4 == 0 && Hout % 16 == 0 && D
 
 int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_target, int num_types, const int64_t *type_off,
                   const float *const *weights, const int32_t *src32, const int32_t *tgt32, const int32_t *pos, float *msg,
-                  void *scratch, cudaStream_t st) {
+                  void *scratch, bool pack, cudaStream_t st) {
     const int Kw = use_target ? 2 * H : H;
     float *w_hi = static_cast<float *>(scratch);
     float *w_lo = reinterpret_cast<float *>(static_cast<char *>(scratch) + ws_slice((size_t)num_types * D * Kw, 4));
-    SplitSrc ss{};
-    ss.num = num_types; ss.elems = D * Kw;
-    for (int t = 0; t < num_types; ++t) ss.w[t] = weights[t];
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        split_weights_kernel<<<148, 256, 0, st>>>(ss, w_hi, w_lo);
+    if (pack) {   // false: `scratch` is a weight cache that already holds the split of these weights
+        SplitSrc ss{};
+        ss.num = num_types; ss.elems = D * Kw;
+        for (int t = 0; t < num_types; ++t) ss.w[t] = weights[t];
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            split_weights_kernel<<<148, 256, 0, st>>>(ss, w_hi, w_lo);
+        }
+        PTGNN_LAUNCHED();
     }
-    PTGNN_LAUNCHED();
 
     MsgPolicy::Params p{};
     int rc = make_map_2d(&p.map_w_hi, w_hi, (uint64_t)num_types * D, Kw, Kw, D < 128 ? D : 128);
@@ -406,22 +408,24 @@ int edge_messages(const float *h_src, const float *h_tgt, int H, int D, int use_
 }
 
 int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D, const float *w_ih, const float *w_hh,
-               const float *b_ih, const float *b_hh, float *out, void *scratch, cudaStream_t st) {
+               const float *b_ih, const float *b_hh, float *out, void *scratch, bool pack, cudaStream_t st) {
     char *s = static_cast<char *>(scratch);
     const size_t s1 = ws_slice((size_t)(H / 32) * 128 * D, 4), s2 = ws_slice((size_t)(H / 32) * 128 * H, 4);
     float *p1_hi = reinterpret_cast<float *>(s), *p1_lo = reinterpret_cast<float *>(s + s1);
     float *p2_hi = reinterpret_cast<float *>(s + 2 * s1), *p2_lo = reinterpret_cast<float *>(s + 2 * s1 + s2);
     float4 *bias4 = reinterpret_cast<float4 *>(s + 2 * s1 + 2 * s2);
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        pack_split_gru_kernel<<<148, 256, 0, st>>>(w_ih, w_hh, H, D, p1_hi, p1_lo, p2_hi, p2_lo);
+    if (pack) {
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            pack_split_gru_kernel<<<148, 256, 0, st>>>(w_ih, w_hh, H, D, p1_hi, p1_lo, p2_hi, p2_lo);
+        }
+        PTGNN_LAUNCHED();
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            pack_gru_bias_kernel<<<(H + 127) / 128, 128, 0, st>>>(b_ih, b_hh, H, bias4);
+        }
+        PTGNN_LAUNCHED();
     }
-    PTGNN_LAUNCHED();
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        pack_gru_bias_kernel<<<(H + 127) / 128, 128, 0, st>>>(b_ih, b_hh, H, bias4);
-    }
-    PTGNN_LAUNCHED();
     GruPolicy::Params p{};
     const uint64_t prow = (uint64_t)(H / 32) * 128;
     int rc = make_map_2d(&p.map_agg, agg, num_nodes, D, D, 128);

@@ -147,6 +147,9 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         self.__edge_feature_dimension = edge_feature_dimension
         self.__aggregation_fn = message_aggregation_function
         self.__dropout = nn.Dropout(p=dropout_rate)
+        # device copies of the parameters in the kernels' working formats, keyed by the parameters' storage + version
+        # counters (see _weight_cache): derived once per set of parameter values instead of once per call
+        self._derived_weights = {}
 
     def forward(
         self,
@@ -182,29 +185,76 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         b_ih, b_hh = N.require_cuda(gru.bias_ih, "bias_ih", torch.float32), N.require_cuda(gru.bias_hh, "bias_hh", torch.float32)
 
         lib = N.lib()
+        params = weights + [w_ih, w_hh, b_ih, b_hh]
         if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
+            cache, valid = self._weight_cache("bf16", lib.ptgnn_b200_gated_weight_cache_bytes_bf16(plan.num_types, H, D), params, h.device)
             ws_bytes = lib.ptgnn_b200_gated_workspace_bytes_bf16(num_nodes, plan.num_edges, plan.num_types, H, D)
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
             out = torch.empty_like(h)
             with torch.cuda.device(h.device):
-                rc = lib.ptgnn_b200_gated_forward_bf16(
+                rc = lib.ptgnn_b200_gated_forward_cached_bf16(
                     N.ptr(h), N.ptr(gsrc), num_nodes, H, D, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
                     N.ptr(plan.src32), N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce,
-                    N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+                    N.ptr(out), N.ptr(ws), ws_bytes, N.ptr(cache), 0 if cache is None else cache.numel(), int(valid),
+                    N.current_stream(h.device),
                 )
-            N.check(rc, "ptgnn_b200_gated_forward_bf16")
+            N.check(rc, "ptgnn_b200_gated_forward_cached_bf16")
+            self._weight_cache_filled("bf16", h.device)
             return out
+        cache, valid = self._weight_cache("f32", lib.ptgnn_b200_gated_weight_cache_bytes(plan.num_types, H, D), params, h.device)
         ws_bytes = lib.ptgnn_b200_gated_workspace_bytes(num_nodes, plan.num_edges, plan.num_types, H, D)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
         out = torch.empty_like(h)
         with torch.cuda.device(h.device):
-            rc = lib.ptgnn_b200_gated_forward_f32(
+            rc = lib.ptgnn_b200_gated_forward_cached_f32(
                 N.ptr(h), N.ptr(gsrc), num_nodes, H, D, plan.num_types, plan.type_off_c, N.ptr(plan.row_ptr), N.ptr(plan.pos),
                 N.ptr(plan.src32), N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce,
-                N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+                N.ptr(out), N.ptr(ws), ws_bytes, N.ptr(cache), 0 if cache is None else cache.numel(), int(valid),
+                N.current_stream(h.device),
             )
-        N.check(rc, "ptgnn_b200_gated_forward_f32")
+        N.check(rc, "ptgnn_b200_gated_forward_cached_f32")
+        self._weight_cache_filled("f32", h.device)
         return out
+
+    # ---- derived-weight cache ------------------------------------------------------------------------------------------
+    def _weight_cache(self, kind: str, nbytes: int, params: List[torch.Tensor], device: torch.device):
+        """Returns (buffer or None, valid).  The buffer holds the kernels' working copies of the parameters (TF32 hi/lo
+        splits and the gate-blocked GRU packing, or their bf16 versions); it is valid while no parameter has been
+        modified in place (`Tensor._version`), re-assigned (`data_ptr`) or moved since the call that filled it.  All
+        uses are ordered on the layer's CUDA stream; a call on a different stream refills the buffer."""
+        if nbytes <= 0:
+            return None, False
+        stream = torch.cuda.current_stream(device).cuda_stream
+        def version(p: torch.Tensor):
+            try:
+                return p._version
+            except RuntimeError:        # inference tensors carry no version counter: never reuse
+                return object()
+
+        key = (tuple((p.data_ptr(), version(p)) for p in params), nbytes, stream)
+        entry = self._derived_weights.get((kind, device))
+        if entry is None or entry["buf"].numel() != nbytes:
+            entry = {"buf": torch.empty(nbytes, dtype=torch.uint8, device=device), "key": None, "pending": None}
+            self._derived_weights[(kind, device)] = entry
+        # eval mode only: in-place edits made through `param.data` do not move the version counter, and training loops
+        # are where those happen -- in training mode the copies are simply re-derived every call
+        valid = (not self.training) and entry["key"] == key
+        entry["pending"] = key
+        return entry["buf"], valid
+
+    def invalidate_weight_cache(self) -> None:
+        """Forget the derived copies (needed only after editing parameters through `.data` in eval mode)."""
+        self._derived_weights = {}
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_derived_weights"] = {}      # device scratch, not part of the module's state
+        return state
+
+    def _weight_cache_filled(self, kind: str, device: torch.device) -> None:
+        entry = self._derived_weights.get((kind, device))
+        if entry is not None and entry["pending"] is not None:
+            entry["key"], entry["pending"] = entry["pending"], None
 
     @property
     def input_state_dimension(self) -> int:
