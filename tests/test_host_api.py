@@ -101,3 +101,54 @@ def test_container_metrics_protocol():
     expanded = gnn.expand_adjacency(raw, 4, torch.device("cpu"))
     assert len(raw) == 1 and len(expanded) == 3  # caller's list is NOT mutated
     assert torch.equal(expanded[1][0], raw[0][1]) and torch.equal(expanded[2][0], torch.arange(4))
+
+
+def test_weight_cache_bookkeeping_without_gpu(monkeypatch):
+    """The derived-weight cache is keyed on (data_ptr, version) of every parameter: reuse only while nothing changed, never
+    in training mode, never carried through deepcopy / pickling.  (The kernels behind it: tests/test_gpu_weight_cache.py.)"""
+    import copy
+
+    import ptgnn_b200 as P
+
+    class _Stream:
+        cuda_stream = 0
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    layer = P.GatedMessagePassingLayer(64, 64, 2, "sum").eval()
+    params = list(layer.parameters())
+    dev = torch.device("cpu")
+    buf, valid = layer._weight_cache("f32", 1024, params, dev)
+    assert buf is not None and not valid
+    layer._weight_cache_filled("f32", dev)
+    buf2, valid = layer._weight_cache("f32", 1024, params, dev)
+    assert valid and buf2 is buf
+    layer._weight_cache_filled("f32", dev)
+    with torch.no_grad():
+        params[0].mul_(2.0)                                   # what load_state_dict / an optimiser step does
+    assert layer._weight_cache("f32", 1024, params, dev)[1] is False
+    layer._weight_cache_filled("f32", dev)
+    assert layer._weight_cache("f32", 1024, params, dev)[1] is True
+    layer._weight_cache_filled("f32", dev)
+    layer.train()
+    assert layer._weight_cache("f32", 1024, params, dev)[1] is False       # never trusted in training mode
+    layer.eval()
+    assert layer._weight_cache("f32", 0, params, dev) == (None, False)     # nothing to cache for these dims
+    assert copy.deepcopy(layer)._derived_weights == {}
+    assert not any("derived" in k for k in layer.state_dict())
+    layer.invalidate_weight_cache()
+    assert layer._weight_cache("f32", 1024, params, dev)[1] is False
+
+
+def test_bench_clock_summary_decodes_nvml_reason_bits():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    assert s.summary()["sm_mhz"] is None
+    s.sm_max, s.source = 1965, "nvml"
+    s.samples = [(1965, 300.0, 0x0), (1950, 320.0, 0x4), (1965, 310.0, 0x1), (1700, 330.0, 0x40)]
+    out = s.summary()
+    assert out["sm_mhz"] == 1965 and out["sm_max_mhz"] == 1965 and out["samples"] == 4
+    assert out["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"] and out["power_w_max"] == 330.0
