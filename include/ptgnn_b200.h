@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PTGNN_B200_ABI_VERSION 1
+#define PTGNN_B200_ABI_VERSION 2
 #define PTGNN_MAX_EDGE_TYPES 128 /* etype is stored as uint8 in the plan; 128 keeps launch params < 4 KB */
 
 enum {
@@ -75,7 +75,8 @@ int ptgnn_b200_kernel_timing_read(double *ms /*[host]*/, int64_t *launches /*[ho
  *   src_sorted[E]    source node of the edge at sorted position j
  *   etype_sorted[E]  edge type of the edge at sorted position j
  *   src32/tgt32[E]   the int64 inputs down-converted, edge-id order
- *   status[1]        number of out-of-range indices seen (they are clamped to 0); 0 = valid
+ *   status[1]        number of out-of-range indices seen (they are clamped to 0); 0 = valid.  Any device-accessible
+ *                    int32: device memory, or pinned host memory the caller can poll without synchronising
  * ---------------------------------------------------------------------------------------------- */
 size_t ptgnn_b200_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes /* bound for src ids; <= 0: num_nodes */,
@@ -99,11 +100,12 @@ int ptgnn_b200_segment_reduce_f32(const float *messages, const int32_t *row_ptr,
                                   int64_t *arg_out, void *stream);
 
 /* One-shot torch_scatter.scatter drop-in: builds a single-type plan from the int64 `index` and reduces.
- * workspace >= ptgnn_b200_scatter_workspace_bytes(N, E). */
+ * workspace >= ptgnn_b200_scatter_workspace_bytes(N, E).  status (optional, device-accessible int32): receives the number of
+ * indices outside [0, num_nodes) (they are routed to row 0; the reference raises / asserts in that case). */
 size_t ptgnn_b200_scatter_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, int64_t num_edges, int32_t dim, int64_t num_nodes,
-                           int32_t reduce, float *out, int64_t *arg_out, void *workspace, size_t workspace_bytes,
-                           void *stream);
+                           int32_t reduce, float *out, int64_t *arg_out, int32_t *status, void *workspace,
+                           size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GatedMessagePassingLayer.forward (gatedmessagepassing.py:37-69), eval mode, no edge features:
@@ -201,6 +203,66 @@ int ptgnn_b200_mlp_forward_bf16(const uint16_t *node_states, const uint16_t *gat
                                 const float *ln_weight, const float *ln_bias, float ln_eps, const float *dense_weight,
                                 const float *dense_bias, int32_t dense_activation, uint16_t *out_states, void *workspace,
                                 size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused aggregation (round 2): gather -> per-type Linear -> segmented reduce in ONE kernel; the [E, D]
+ * message tensor of gatedmessagepassing.py:64 / mlpmessagepassing.py:100-112 is never materialised.
+ *
+ * Block plan: the edges sorted, stably, by (target block, edge type, target), blocks of `block_targets`
+ * (<= 240, multiple of 8; ptgnn_b200_block_plan_block_targets recommends one) consecutive target nodes:
+ *   group_off[ceil(N / B) * T + 1]  sorted-edge offsets of the (block, type) groups
+ *   src_f[E]                        source node of the edge at sorted position j
+ *   tl_f[E]                         target of that edge, relative to its block's first node
+ * Built from the src32 / tgt32 arrays of ptgnn_b200_plan_build, once per minibatch, reused by all layers.
+ * `status` (optional): two device-accessible int32 words (device memory or pinned host memory); the layer kernels
+ * set status[0] = 1 if a node state, status[1] = 1 if an edge weight is outside the fp16 range of the fp32-exact
+ * 3xFP16 split (|x| >= 65504, inf, NaN): the result is then not valid, use the unfused entry points.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t block_targets;
+    const int32_t *group_off;
+    const int32_t *src_f;
+    const uint8_t *tl_f;
+    int32_t *status;
+} ptgnn_b200_block_plan;
+
+int32_t ptgnn_b200_block_plan_block_targets(int64_t num_nodes);
+size_t ptgnn_b200_block_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types, int32_t block_targets);
+int ptgnn_b200_block_plan_build(int64_t num_nodes, int32_t num_types, const int64_t *type_off /*[host]*/,
+                                const int32_t *src32, const int32_t *tgt32, int32_t block_targets, int32_t *group_off,
+                                int32_t *src_f, uint8_t *tl_f, void *workspace, size_t workspace_bytes, void *stream);
+
+/* 1 if these dimensions run on the fused kernel (message_dim == 128; state_dim in {64, 128} for fp32 states,
+ * {64, 128, 256} for bf16 states); otherwise use the unfused entry points above. */
+int32_t ptgnn_b200_fused_supported(int32_t bf16_states, int32_t state_dim, int32_t message_dim);
+
+/* GatedMessagePassingLayer.forward through the fused kernel.  Same contract as ptgnn_b200_gated_forward_cached_{f32,bf16}
+ * (node_states / gather_states / out_states are fp32 when bf16_states == 0, bf16 otherwise; `row_ptr` = CSR offsets of the
+ * edge plan, used by reduce = mean); the edge arrays come from the block plan.  fp32 states are computed fp32-exactly with
+ * three fp16 tensor-core products per term ("3xFP16", see csrc/fused_mp.cuh). */
+size_t ptgnn_b200_gated_fused_workspace_bytes(int32_t bf16_states, int64_t num_nodes, int64_t num_source_nodes,
+                                              int32_t num_types, int32_t state_dim, int32_t message_dim);
+size_t ptgnn_b200_gated_fused_weight_cache_bytes(int32_t bf16_states, int32_t num_types, int32_t state_dim, int32_t message_dim);
+int ptgnn_b200_gated_forward_fused(int32_t bf16_states, const void *node_states, const void *gather_states /* NULL: node_states */,
+                                   int64_t num_nodes, int64_t num_source_nodes, int32_t state_dim, int32_t message_dim,
+                                   int32_t num_types, const ptgnn_b200_block_plan *block_plan, const int32_t *row_ptr,
+                                   const float *const *edge_weights /*[host] T device pointers, fp32*/, const float *gru_w_ih,
+                                   const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh, int32_t reduce,
+                                   void *out_states, void *workspace, size_t workspace_bytes, void *weight_cache,
+                                   size_t weight_cache_bytes, int32_t cache_valid, void *stream);
+
+/* MlpMessagePassingLayer.forward through the fused kernel (contract of ptgnn_b200_mlp_forward_{f32,bf16}); the message
+ * activation and the LayerNorm run in the fused kernel's write-out. */
+size_t ptgnn_b200_mlp_fused_workspace_bytes(int32_t bf16_states, int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
+                                            int32_t in_dim, int32_t message_dim, int32_t out_dim, int32_t use_target_state);
+int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *node_states, const void *gather_states /* NULL: node_states */,
+                                 int64_t num_nodes, int64_t num_source_nodes, int32_t in_dim, int32_t message_dim,
+                                 int32_t out_dim, int32_t num_types, const ptgnn_b200_block_plan *block_plan,
+                                 const int32_t *row_ptr, const float *const *edge_weights /*[host] T device pointers, fp32*/,
+                                 int32_t use_target_state, int32_t reduce, int32_t message_activation, const float *ln_weight,
+                                 const float *ln_bias, float ln_eps, const float *dense_weight, const float *dense_bias,
+                                 int32_t dense_activation, void *out_states, void *workspace, size_t workspace_bytes,
+                                 void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry point (used for the end-to-end measurement): all pointers are HOST

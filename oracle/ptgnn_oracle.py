@@ -247,3 +247,27 @@ def edge_plan(adjacency_lists: Adjacency, num_nodes: int) -> Dict[str, np.ndarra
         "tgt32": tgt.astype(np.int32),
         "type_off": type_off.astype(np.int32),
     }
+
+
+def block_plan(adjacency_lists: Adjacency, num_nodes: int, block_targets: int) -> Dict[str, np.ndarray]:
+    """Edge order of the fused aggregation kernel (``ptgnn_b200_block_plan_build``; no reference counterpart): the
+    concatenated edges sorted, STABLY, by (target block, edge type, target) with blocks of ``block_targets`` consecutive
+    nodes.  Inside one target the edges therefore keep the reference's scatter order (type-major, then list order).
+
+    * ``group_off[b * T + t]`` = sorted position of the first edge of (block b, type t); last entry = E
+    * ``src_f[j]``, ``tl_f[j]`` = source node / (target - block start) of the edge at sorted position ``j``
+    """
+    T = len(adjacency_lists)
+    counts = np.array([int(a[0].shape[0]) for a in adjacency_lists], dtype=np.int64)
+    src = np.concatenate([a[0].numpy() for a in adjacency_lists]) if T else np.zeros(0, np.int64)
+    tgt = np.concatenate([a[1].numpy() for a in adjacency_lists]) if T else np.zeros(0, np.int64)
+    etype = np.repeat(np.arange(T, dtype=np.int64), counts)
+    B = int(block_targets)
+    nblk = (num_nodes + B - 1) // B
+    blk, tl = tgt // B, tgt % B
+    key = (blk * T + etype) * B + tl
+    perm = np.argsort(key, kind="stable")
+    group_off = np.zeros(nblk * T + 1, dtype=np.int64)
+    np.cumsum(np.bincount(blk * T + etype, minlength=nblk * T), out=group_off[1:])
+    return {"group_off": group_off.astype(np.int32), "src_f": src[perm].astype(np.int32), "tl_f": tl[perm].astype(np.uint8),
+            "perm": perm.astype(np.int32)}

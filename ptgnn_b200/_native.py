@@ -28,7 +28,7 @@ SIGNATURES = {
     "ptgnn_b200_plan_build": (ctypes.c_int, [c_i64, c_i64, c_i32, c_void_p, c_void_p, c_void_p] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_segment_reduce_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
     "ptgnn_b200_scatter_workspace_bytes": (c_size_t, [c_i64, c_i64]),
-    "ptgnn_b200_scatter_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptgnn_b200_scatter_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptgnn_b200_gated_workspace_bytes": (c_size_t, [c_i64, c_i64, c_i32, c_i32, c_i32]),
     "ptgnn_b200_gated_forward_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                     c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -51,10 +51,31 @@ SIGNATURES = {
     "ptgnn_b200_mlp_forward_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                    c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_f32, c_void_p, c_void_p, c_i32,
                                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptgnn_b200_block_plan_block_targets": (c_i32, [c_i64]),
+    "ptgnn_b200_block_plan_workspace_bytes": (c_size_t, [c_i64, c_i64, c_i32, c_i32]),
+    "ptgnn_b200_block_plan_build": (ctypes.c_int, [c_i64, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptgnn_b200_fused_supported": (c_i32, [c_i32, c_i32, c_i32]),
+    "ptgnn_b200_gated_fused_workspace_bytes": (c_size_t, [c_i32, c_i64, c_i64, c_i32, c_i32, c_i32]),
+    "ptgnn_b200_gated_fused_weight_cache_bytes": (c_size_t, [c_i32, c_i32, c_i32, c_i32]),
+    "ptgnn_b200_gated_forward_fused": (ctypes.c_int, [c_i32, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p,
+                                                      c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_size_t, c_void_p,
+                                                      c_size_t, c_i32, c_void_p]),
+    "ptgnn_b200_mlp_fused_workspace_bytes": (c_size_t, [c_i32, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    "ptgnn_b200_mlp_forward_fused": (ctypes.c_int, [c_i32, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_void_p,
+                                                    c_i32, c_i32, c_i32, c_void_p, c_void_p, c_f32, c_void_p, c_void_p, c_i32, c_void_p, c_void_p,
+                                                    c_size_t, c_void_p]),
     "ptgnn_b200_gated_gnn_forward_host_f32": (ctypes.c_int, [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_i32,
                                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p]),
 }
 
+
+
+class BlockPlanStruct(ctypes.Structure):
+    """`ptgnn_b200_block_plan` of include/ptgnn_b200.h."""
+    _fields_ = [("block_targets", c_i32), ("group_off", c_void_p), ("src_f", c_void_p), ("tl_f", c_void_p), ("status", c_void_p)]
+
+
+ABI_VERSION = 2
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -76,7 +97,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.ptgnn_b200_abi_version() != 1:
+        if handle.ptgnn_b200_abi_version() != ABI_VERSION:
             raise NativeLibraryError("libptgnn_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

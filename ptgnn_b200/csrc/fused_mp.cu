@@ -1,0 +1,681 @@
+// Fused gather -> per-edge-type Linear -> segmented reduce on tcgen05 (see fused_mp.cuh for the design).
+#include "fused_mp.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace ptgnn {
+namespace fused {
+
+using tc::mbar_arrive;
+using tc::mbar_init;
+using tc::mbar_wait;
+
+// ---- geometry ------------------------------------------------------------------------------------------------------
+constexpr int NUM_THREADS = 12 * 32;
+constexpr int MMA_WARP = 4;
+constexpr int GATHER_WARP0 = 5, GATHER_THREADS = 64;
+constexpr int SCHED_WARP = 7;
+constexpr int EPI_WARP0 = 8, EPI_THREADS = 128;
+constexpr int NUM_CONSUMER_WARPS = 4 + 1 + 2 + 4;      // weight loaders, MMA, gatherers, epilogue (scheduler table readers)
+constexpr int NUM_SLOTS = 3, LOOKAHEAD = 2;
+constexpr int SLOT_BYTES = 32768;
+constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
+constexpr int META_RING = 8;
+constexpr int SCHED_RING = 4;
+constexpr int MID_REGS = 80, EPI_REGS = 200;      // weight loaders keep the launch bound (168): (168 + 80 + 200) * 128 = 57344 <= 65536
+constexpr int ACC_TMEM_OFF = 256;                               // weight buffers below, accumulators above
+constexpr int EPI_BAR_ID = 2;
+
+struct Meta {                     // per sub-group: what the epilogue needs to know about the accumulator columns
+    int32_t tloff[128];           // byte offset of the column's target row inside agg_s (0 for columns >= n)
+    uint32_t endmask[4];          // bit c: column c is the last edge of its (target, type) segment
+    int32_t n, pad[3];
+};
+struct Sched {                    // one target block: its id and the T+1 sorted-edge offsets of its (block, type) groups
+    int32_t blk, pad[3];
+    int32_t off[PTGNN_MAX_EDGE_TYPES + 4];
+};
+constexpr int AGG_OFF = RING_BYTES;
+__host__ __device__ constexpr int agg_bytes(int B) { return B * kD * 4; }
+constexpr int SMEM_TAIL = META_RING * (int)sizeof(Meta) + SCHED_RING * (int)sizeof(Sched) + 256 /*barriers*/;
+constexpr int smem_bytes(int B) { return 1024 + RING_BYTES + agg_bytes(B) + SMEM_TAIL; }
+static_assert(smem_bytes(kMaxBlockTargets) <= 232448, "shared memory budget");
+
+struct Params {
+    const unsigned char *src_rows, *tgt_rows;
+    const uint4 *wpack;
+    const int32_t *group_off, *src_f;
+    const uint8_t *tl_f;
+    const int32_t *row_ptr;
+    void *out;
+    int num_nodes, num_blocks, B, T, reduce, out_bf16;
+    Epilogue epi;
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32cols_u32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ uint32_t swz(int row, int q) { return (uint32_t)(row * 128 + ((q ^ (row & 7)) << 4)); }
+
+// ---- the (block, group, sub-group, segment) walk every role performs in the same order -----------------------------------
+struct Step { int blk, t, e, n, seg; bool first_sub, last_sub; };
+template <int NSEG>
+struct StepGen {
+    const Sched *sched;
+    uint64_t *sfull, *sempty;
+    int T, nmax, lane;
+    uint32_t it = 0;
+    const Sched *tab = nullptr;
+    int blk = -1, t = 0, e0 = 0, e = 0, e1 = 0, seg = 0;
+    bool in_block = false;
+    // 0: `s` is the next step | 1: the block s.blk has no more steps | 2: no more blocks
+    __device__ __forceinline__ int next(Step &s) {
+        for (;;) {
+            if (!in_block) {
+                const uint32_t r = it % SCHED_RING;
+                mbar_wait(&sfull[r], (it / SCHED_RING) & 1);
+                tab = &sched[r];
+                blk = tab->blk;
+                if (blk < 0) return 2;
+                in_block = true;
+                t = -1; e = e1 = 0; seg = 0;
+            }
+            if (e < e1) {
+                s.blk = blk; s.t = t; s.e = e; s.n = min(nmax, e1 - e); s.seg = seg;
+                s.first_sub = e == e0; s.last_sub = e + nmax >= e1;
+                if (++seg == NSEG) { seg = 0; e += nmax; }
+                return 0;
+            }
+            ++t;
+            while (t < T && tab->off[t + 1] == tab->off[t]) ++t;
+            if (t >= T) {
+                in_block = false;
+                s.blk = blk;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[it % SCHED_RING]);     // this warp no longer reads the table
+                ++it;
+                return 1;
+            }
+            e0 = e = tab->off[t]; e1 = tab->off[t + 1]; seg = 0;
+        }
+    }
+};
+
+template <int RED> __device__ __forceinline__ float red_identity() {
+    return RED == PTGNN_REDUCE_MAX ? -FLT_MAX : (RED == PTGNN_REDUCE_MIN ? FLT_MAX : 0.0f);
+}
+template <int RED> __device__ __forceinline__ float red_op(float a, float m) {
+    if (RED == PTGNN_REDUCE_MAX) return m > a ? m : a;      // strict compare: NaN never wins (torch_scatter)
+    if (RED == PTGNN_REDUCE_MIN) return m < a ? m : a;
+    return a + m;
+}
+
+// =====================================================================================================================
+template <int NPROD, int K, int NSEG, int RED>
+__global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const __grid_constant__ Params p) {
+    constexpr int NPART = NPROD == 3 ? 2 : 1;                      // hi | lo' parts of a row / of the weights
+    constexpr int NMAX = NPROD == 3 ? 64 : (K <= 128 ? 128 : 64);  // edges per MMA (accumulator columns)
+    constexpr int ROW_BYTES = K * 2 * NPART;                       // one packed state row
+    constexpr int KCH = K / 64;                                    // 128-byte swizzled chunks per part
+    constexpr int NT = NPART * KCH;                                // operand tiles per slot
+    constexpr int TILE_BYTES = NMAX * 128;
+    static_assert(NT * TILE_BYTES <= SLOT_BYTES, "slot size");
+    constexpr int WPART_COLS = K / 2;                              // TMEM columns of one weight part
+    constexpr int WBUF_COLS = NPART * WPART_COLS;
+    static_assert(2 * WBUF_COLS <= ACC_TMEM_OFF, "weight buffers");
+    constexpr int ACC_COLS = 128;                                  // per accumulator set: main [0, NMAX) | correction [64, 128)
+    static_assert(NPROD == 1 || NMAX == 64, "correction accumulator offset");
+    constexpr uint32_t FMT = NPROD == 3 ? 0u /*F16*/ : tc::FMT_BF16;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *agg_s = reinterpret_cast<float *>(ring + AGG_OFF);
+    unsigned char *tail = ring + AGG_OFF + agg_bytes(p.B);
+    Meta *meta_ring = reinterpret_cast<Meta *>(tail);
+    Sched *sched = reinterpret_cast<Sched *>(tail + META_RING * sizeof(Meta));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + META_RING * sizeof(Meta) + SCHED_RING * sizeof(Sched));
+    uint64_t *x_full = bars, *x_empty = bars + 3, *w_full = bars + 6, *w_empty = bars + 8, *acc_full = bars + 10,
+             *acc_empty = bars + 12, *sched_full = bars + 14, *sched_empty = bars + 18;
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(bars + 22);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_SLOTS; ++s) { mbar_init(&x_full[s], GATHER_THREADS); mbar_init(&x_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&w_full[b], 128); mbar_init(&w_empty[b], 1);
+            mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4);
+        }
+        for (int r = 0; r < SCHED_RING; ++r) { mbar_init(&sched_full[r], 1); mbar_init(&sched_empty[r], NUM_CONSUMER_WARPS); }
+        tc::mbar_init_fence();
+    }
+    if (warp == 0) tc::tmem_alloc<512>(tmem_base_smem);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_smem, 0);
+    const int T = p.T;
+
+    if (warp < 4) {
+        // ============================================ WEIGHT LOADERS ============================================
+        // Thread d owns TMEM lane d = row d of W_t.  The packed weights are laid out so that a warp-wide 16-byte load is one
+        // contiguous 512-byte burst: wpack[(((t * NSEG + seg) * NPART + part) * (K / 8) + c4) * 128 + d] = columns 4 c4 .. 4 c4 + 3.
+        // All loads of a (type, segment) are in flight before the buffer's release is awaited.
+        const int d = warp * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
+        uint32_t wl = 0;
+        Step s;
+        for (;;) {
+            const int ev = gen.next(s);
+            if (ev == 2) break;
+            if (ev == 1 || !s.first_sub) continue;
+            const uint4 *src = p.wpack + ((size_t)(s.t * NSEG + s.seg) * NPART * (K / 8)) * 128 + d;
+            uint32_t w[NPART][K / 2];
+#pragma unroll
+            for (int part = 0; part < NPART; ++part)
+#pragma unroll
+                for (int c4 = 0; c4 < K / 8; ++c4) {
+                    const uint4 v = ldg_nc_u4(src + (size_t)(part * (K / 8) + c4) * 128);
+                    w[part][4 * c4] = v.x; w[part][4 * c4 + 1] = v.y; w[part][4 * c4 + 2] = v.z; w[part][4 * c4 + 3] = v.w;
+                }
+            const uint32_t wb = wl & 1;
+            mbar_wait(&w_empty[wb], ((wl >> 1) & 1) ^ 1);        // the MMAs that read this buffer two loads ago are done
+            tc::tc_fence_after_sync();
+#pragma unroll
+            for (int part = 0; part < NPART; ++part)
+#pragma unroll
+                for (int j = 0; j < WPART_COLS / 32; ++j) {
+                    uint32_t chunk[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) chunk[i] = w[part][32 * j + i];
+                    tmem_st_32cols_u32(tmem_lane + wb * WBUF_COLS + part * WPART_COLS + 32 * j, chunk);
+                }
+            tc::tmem_st_wait();
+            tc::tc_fence_before_sync();
+            mbar_arrive(&w_full[wb]);
+            ++wl;
+        }
+    } else if (warp < 8) {
+        tc::reg_dealloc<MID_REGS>();
+        if (warp == MMA_WARP) {
+            // ============================================ MMA ISSUER ============================================
+            const bool leader = tc::elect_one();
+            StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
+            uint32_t xs = 0, sg = 0, wl = 0, wl0 = 0;
+            Step s;
+            for (;;) {
+                const int ev = gen.next(s);
+                if (ev == 2) break;
+                if (ev == 1) continue;
+                if (s.first_sub && s.seg == 0) { wl0 = wl; wl += NSEG; }
+                const uint32_t ab = sg & 1;
+                if (s.seg == 0) {
+                    mbar_wait(&acc_empty[ab], ((sg >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator set
+                }
+                const uint32_t slot = xs % NUM_SLOTS;
+                mbar_wait(&x_full[slot], (xs / NUM_SLOTS) & 1);
+                const uint32_t wli = wl0 + s.seg, wb = wli & 1;
+                if (s.first_sub) mbar_wait(&w_full[wb], (wli >> 1) & 1);
+                tc::tc_fence_after_sync();
+                const uint32_t n16 = (uint32_t)(s.n + 15) & ~15u;
+                const uint32_t idesc = tc::make_instr_desc(FMT, 128, n16);
+                const uint32_t slot_addr = smem_u32(ring + slot * SLOT_BYTES);
+                const uint32_t d_main = tmem_base + ACC_TMEM_OFF + ab * ACC_COLS, d_corr = d_main + 64;
+                const uint32_t a_base = tmem_base + wb * WBUF_COLS;
+#pragma unroll
+                for (int ks = 0; ks < K / 16; ++ks) {
+                    const int kc = ks >> 2, kk = ks & 3;
+                    const uint32_t acc = (s.seg == 0 && ks == 0) ? 0u : 1u;
+                    const uint64_t x_hi = tc::make_smem_desc_sw128(slot_addr + kc * TILE_BYTES) + kk * 2;
+                    if (NPROD == 3) {
+                        const uint64_t x_lo = tc::make_smem_desc_sw128(slot_addr + (KCH + kc) * TILE_BYTES) + kk * 2;
+                        if (leader) {
+                            // x * w ~= hi*hi (main) + 2^-11 (hi*lo' + lo'*hi) (correction accumulator, scaled by 2^11)
+                            mma_f16_ts(d_main, a_base + ks * 8, x_hi, idesc, acc);
+                            mma_f16_ts(d_corr, a_base + ks * 8, x_lo, idesc, acc);
+                            mma_f16_ts(d_corr, a_base + WPART_COLS + ks * 8, x_hi, idesc, 1u);
+                        }
+                    } else {
+                        if (leader) mma_f16_ts(d_main, a_base + ks * 8, x_hi, idesc, acc);
+                    }
+                }
+                if (leader) tc::mma_commit(&x_empty[slot]);
+                if (leader && s.last_sub) tc::mma_commit(&w_empty[wb]);
+                if (leader && s.seg == NSEG - 1) tc::mma_commit(&acc_full[ab]);
+                __syncwarp();
+                ++xs;
+                if (s.seg == NSEG - 1) ++sg;
+            }
+        } else if (warp == SCHED_WARP) {
+            // ============================================ SCHEDULER ============================================
+            // Publishes, a few blocks ahead, the group-offset row of each target block this CTA owns (static round robin).
+            for (uint32_t i = 0;; ++i) {
+                const uint32_t r = i % SCHED_RING;
+                mbar_wait(&sched_empty[r], ((i / SCHED_RING) & 1) ^ 1);
+                const long long blk = (long long)blockIdx.x + (long long)i * gridDim.x;
+                const bool valid = blk < p.num_blocks;
+                Sched *e = &sched[r];
+                if (valid) {
+                    for (int t = lane; t <= T; t += 32) e->off[t] = __ldg(p.group_off + blk * T + t);
+                }
+                if (lane == 0) e->blk = valid ? (int)blk : -1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sched_full[r]);
+                if (!valid) break;
+            }
+        } else {
+            // ============================================ ROW GATHERERS ============================================
+            // 64 threads copy the packed state rows of every (sub-group, segment) into a ring slot with 16-byte cp.async:
+            // thread g moves piece q = g & 7 of every 128-byte chunk of rows (g >> 3) + 8 i.  Tile (part, kc) of a slot holds
+            // columns [64 kc, 64 kc + 64) of that part, SWIZZLE_128B K-major -- the MMA's B operand.  Rows >= n are left as
+            // they are: an accumulator column depends on its own B row only, and the epilogue never reads those columns.
+            const int g = (int)threadIdx.x - GATHER_WARP0 * 32;
+            const int q = g & 7, rsub = g >> 3;
+            StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
+            uint32_t c_issue = 0, c_done = 0, sgc = 0;
+            bool more = true;
+            auto issue_next = [&]() {
+                Step s;
+                int ev;
+                do { ev = gen.next(s); } while (ev == 1);
+                if (ev == 2) { more = false; return; }
+                int idx[NMAX / 8];
+                if (s.seg == 0) {
+#pragma unroll
+                    for (int i = 0; i < NMAX / 8; ++i) {
+                        const int r = rsub + 8 * i;
+                        idx[i] = r < s.n ? __ldg(p.src_f + s.e + r) : -1;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NMAX / 8; ++i) {
+                        const int r = rsub + 8 * i;
+                        idx[i] = r < s.n ? s.blk * p.B + (int)__ldg(p.tl_f + s.e + r) : -1;
+                    }
+                }
+                if (s.seg == 0) {       // column metadata for the epilogue (columns g and g + 64)
+                    Meta *m = &meta_ring[sgc % META_RING];
+#pragma unroll
+                    for (int half = 0; half < NMAX / 64; ++half) {
+                        const int c = g + 64 * half;
+                        int tl = 0;
+                        bool end = false;
+                        if (c < s.n) {
+                            tl = (int)__ldg(p.tl_f + s.e + c);
+                            end = c == s.n - 1 || (int)__ldg(p.tl_f + s.e + c + 1) != tl;
+                        }
+                        m->tloff[c] = tl * (kD * 4);
+                        const uint32_t word = __ballot_sync(0xffffffffu, end);
+                        if (lane == 0) m->endmask[c >> 5] = word;
+                    }
+                    if (g == 0) m->n = s.n;
+                    ++sgc;
+                }
+                const uint32_t slot = c_issue % NUM_SLOTS;
+                mbar_wait(&x_empty[slot], ((c_issue / NUM_SLOTS) & 1) ^ 1);
+                const unsigned char *rows = s.seg == 0 ? p.src_rows : p.tgt_rows;
+                const uint32_t sbase = smem_u32(ring + slot * SLOT_BYTES) + swz(rsub, q);
+#pragma unroll
+                for (int i = 0; i < NMAX / 8; ++i) {
+                    if (idx[i] >= 0) {
+                        const unsigned char *src = rows + (size_t)idx[i] * ROW_BYTES + q * 16;
+#pragma unroll
+                        for (int ti = 0; ti < NT; ++ti)
+                            cp_async16(sbase + ti * TILE_BYTES + i * 1024, src + (ti / KCH) * (K * 2) + (ti % KCH) * 128, 16);
+                    }
+                }
+                ++c_issue;
+            };
+#pragma unroll
+            for (int i = 0; i < LOOKAHEAD; ++i) {
+                if (more) issue_next();
+                cp_async_commit();
+            }
+            while (c_done < c_issue) {
+                cp_async_wait<LOOKAHEAD - 1>();          // this thread's pieces of step c_done have landed ...
+                tc::fence_proxy_async_smem();            // ... and are visible to the tensor core (async proxy)
+                mbar_arrive(&x_full[c_done % NUM_SLOTS]);
+                ++c_done;
+                if (more) issue_next();
+                cp_async_commit();
+            }
+            cp_async_wait<0>();
+        }
+    } else {
+        // ============================================ EPILOGUE ============================================
+        // Thread d owns message feature d = TMEM lane d and column d of agg_s.  For every accumulator column (edge) in plan
+        // order: value = main (+ 2^-11 correction); at the first edge of a (target, type) segment the running value is
+        // (re)loaded from agg_s[target][d], at the last one it is stored back -- a target's messages are accumulated one by one
+        // in the reference's order, across types and sub-groups.  All agg_s reads of a 32-column batch are issued up front.
+        tc::reg_alloc<EPI_REGS>();
+        const int ew = warp - EPI_WARP0;
+        const int d = ew * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC_TMEM_OFF;
+        unsigned char *aggcol = reinterpret_cast<unsigned char *>(agg_s + d);
+        const float IDENT = red_identity<RED>();
+        StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
+        for (int r = 0; r < p.B; ++r) agg_s[r * kD + d] = IDENT;
+        uint32_t sg = 0;
+        float acc = IDENT;
+        Step s;
+        for (;;) {
+            const int ev = gen.next(s);
+            if (ev == 2) break;
+            if (ev == 0) {
+                if (s.seg != NSEG - 1) continue;
+                const uint32_t ab = sg & 1;
+                mbar_wait(&acc_full[ab], (sg >> 1) & 1);
+                tc::tc_fence_after_sync();
+                const Meta *m = &meta_ring[sg % META_RING];
+                const int n = s.n;
+                uint32_t carry = 1u;                       // the first column of a sub-group always (re)loads its target's value
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    uint32_t vm[32], vc[32];
+                    tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
+                    if (NPROD == 3) tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
+                    int off[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int4 o = *reinterpret_cast<const int4 *>(&m->tloff[c0 + 4 * j]);
+                        off[4 * j] = o.x; off[4 * j + 1] = o.y; off[4 * j + 2] = o.z; off[4 * j + 3] = o.w;
+                    }
+                    const uint32_t endw = m->endmask[c0 >> 5];
+                    const uint32_t startw = (endw << 1) | carry;
+                    carry = endw >> 31;
+                    float pre[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) pre[c] = *reinterpret_cast<const float *>(aggcol + off[c]);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float v = __uint_as_float(vm[c]);
+                        if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
+                        else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
+                        if ((startw >> c) & 1u) acc = pre[c];
+                        acc = red_op<RED>(acc, v);
+                        if ((endw >> c) & 1u) *reinterpret_cast<float *>(aggcol + off[c]) = acc;
+                    }
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                ++sg;
+                continue;
+            }
+            // ---- block finished: every column of agg_s is final once all four warps are here ----
+            named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+            const int row0 = s.blk * p.B;
+            const int rows = min(p.B, p.num_nodes - row0);
+            for (int r = ew; r < rows; r += 4) {
+                float4 a = *reinterpret_cast<const float4 *>(agg_s + r * kD + lane * 4);
+                const int v = row0 + r;
+                if (RED == PTGNN_REDUCE_MEAN) {
+                    const int cnt = __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
+                    const float c = (float)(cnt < 1 ? 1 : cnt);
+                    a.x /= c; a.y /= c; a.z /= c; a.w /= c;
+                }
+                if (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN) {   // never updated -> 0 (torch_scatter)
+                    if (a.x == IDENT) a.x = 0.0f;
+                    if (a.y == IDENT) a.y = 0.0f;
+                    if (a.z == IDENT) a.z = 0.0f;
+                    if (a.w == IDENT) a.w = 0.0f;
+                }
+                if (p.epi.act != PTGNN_ACT_NONE) {
+                    a.x = apply_act(a.x, p.epi.act); a.y = apply_act(a.y, p.epi.act);
+                    a.z = apply_act(a.z, p.epi.act); a.w = apply_act(a.w, p.epi.act);
+                }
+                if (p.epi.ln_w != nullptr) {       // LayerNorm over the 128 features of the row (same order as reduce.cuh)
+                    float sum = (a.x + a.y) + (a.z + a.w);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float mean = sum / (float)kD;
+                    const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
+                    float qq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                    const float rstd = rsqrtf(qq / (float)kD + p.epi.ln_eps);
+                    const float4 w = *reinterpret_cast<const float4 *>(p.epi.ln_w + lane * 4);
+                    const float4 b = *reinterpret_cast<const float4 *>(p.epi.ln_b + lane * 4);
+                    a.x = dx * rstd * w.x + b.x; a.y = dy * rstd * w.y + b.y;
+                    a.z = dz * rstd * w.z + b.z; a.w = dw * rstd * w.w + b.w;
+                }
+                if (p.out_bf16) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t *>(&lo); pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                    reinterpret_cast<uint2 *>(p.out)[(size_t)v * (kD / 4) + lane] = pk;
+                } else {
+                    reinterpret_cast<float4 *>(p.out)[(size_t)v * (kD / 4) + lane] = a;
+                }
+            }
+            named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+            for (int r = 0; r < p.B; ++r) agg_s[r * kD + d] = IDENT;
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
+// =====================================================================================================================
+// packing kernels
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// x -> (hi, lo') fp16 pair; returns false when |x| is not representable (>= 65504, inf, NaN)
+__device__ __forceinline__ bool split_f16(float x, __half &hi, __half &lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+    return fabsf(x) < 65504.0f;
+}
+
+// fp32 [rows, K] -> rows of 2K fp16: hi[K] | lo'[K].  One thread per 8 consecutive elements (32 bytes in, 2 x 16 bytes out).
+__global__ void __launch_bounds__(256) pack_states_kernel(const float *__restrict__ h, long long rows, int K,
+                                                          uint4 *__restrict__ out, int32_t *__restrict__ status) {
+    const long long total = rows * (K / 8);
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / (K / 8);
+        const int c8 = (int)(i - row * (K / 8));
+        const float4 a = ld_stream_f4(reinterpret_cast<const float4 *>(h + row * K + c8 * 8));
+        const float4 b = ld_stream_f4(reinterpret_cast<const float4 *>(h + row * K + c8 * 8 + 4));
+        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bad |= !split_f16(x[j], hi[j], lo[j]);
+        uint4 vh, vl;
+        vh.x = pack_h2(hi[0], hi[1]); vh.y = pack_h2(hi[2], hi[3]); vh.z = pack_h2(hi[4], hi[5]); vh.w = pack_h2(hi[6], hi[7]);
+        vl.x = pack_h2(lo[0], lo[1]); vl.y = pack_h2(lo[2], lo[3]); vl.z = pack_h2(lo[4], lo[5]); vl.w = pack_h2(lo[6], lo[7]);
+        uint4 *dst = out + row * (K / 4);       // row = 4K bytes = K/4 uint4: hi part first (K/8 uint4), then lo'
+        dst[c8] = vh;
+        dst[K / 8 + c8] = vl;
+    }
+    if (bad && status != nullptr) *reinterpret_cast<volatile int32_t *>(status) = 1;
+}
+
+struct WeightSrc {
+    const float *w[PTGNN_MAX_EDGE_TYPES];
+};
+// out[(((t * nseg + seg) * npart + part) * (K / 8) + c4) * 128 + d] = 8 elements k = seg K + 8 c4 .. + 7 of row d
+template <int NPROD>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ WeightSrc src, int num_types, int K, int nseg,
+                                                           uint4 *__restrict__ out, int32_t *__restrict__ status) {
+    constexpr int NPART = NPROD == 3 ? 2 : 1;
+    const int per_mat = nseg * (K / 8) * 128;             // (seg, c4, d) triples per type
+    const long long total = (long long)num_types * per_mat;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / per_mat);
+        int r = (int)(i - (long long)t * per_mat);
+        const int seg = r / ((K / 8) * 128);
+        r -= seg * (K / 8) * 128;
+        const int c4 = r / 128, d = r % 128;
+        const float *row = src.w[t] + (size_t)d * (nseg * K) + seg * K + c4 * 8;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = row[j];
+        const size_t base = ((size_t)(t * nseg + seg) * NPART) * (K / 8) * 128;
+        if (NPROD == 3) {
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bad |= !split_f16(x[j], hi[j], lo[j]);
+            uint4 vh, vl;
+            vh.x = pack_h2(hi[0], hi[1]); vh.y = pack_h2(hi[2], hi[3]); vh.z = pack_h2(hi[4], hi[5]); vh.w = pack_h2(hi[6], hi[7]);
+            vl.x = pack_h2(lo[0], lo[1]); vl.y = pack_h2(lo[2], lo[3]); vl.z = pack_h2(lo[4], lo[5]); vl.w = pack_h2(lo[6], lo[7]);
+            out[base + (size_t)c4 * 128 + d] = vh;
+            out[base + (size_t)(K / 8 + c4) * 128 + d] = vl;
+        } else {
+            uint4 v;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(x[4], x[5]), p3 = __floats2bfloat162_rn(x[6], x[7]);
+            v.x = *reinterpret_cast<uint32_t *>(&p0); v.y = *reinterpret_cast<uint32_t *>(&p1);
+            v.z = *reinterpret_cast<uint32_t *>(&p2); v.w = *reinterpret_cast<uint32_t *>(&p3);
+            out[base + (size_t)c4 * 128 + d] = v;
+        }
+    }
+    if (bad && status != nullptr) *reinterpret_cast<volatile int32_t *>(status + 1) = 1;
+}
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+bool supported(int nprod, int K, int D, int use_target) {
+    (void)use_target;
+    if (D != kD) return false;
+    if (nprod == 3) return K == 64 || K == 128;
+    if (nprod == 1) return K == 64 || K == 128 || K == 256;
+    return false;
+}
+size_t packed_weight_bytes(int nprod, int num_types, int K, int use_target) {
+    const int nseg = use_target ? 2 : 1, npart = nprod == 3 ? 2 : 1;
+    return ws_slice((size_t)num_types * nseg * npart * (K / 8) * 128, 16);
+}
+size_t packed_state_bytes(int nprod, int64_t rows, int K) {
+    return nprod == 3 ? ws_slice((size_t)rows * K * 4 + 16, 1) : 0;
+}
+int recommended_block_targets(int64_t num_nodes) {
+    // the largest B <= kMaxBlockTargets (multiple of 8) for which the block count is a whole number of 148-CTA waves or less
+    if (num_nodes <= 0) return kMaxBlockTargets;
+    const int64_t waves = ceil_div(num_nodes, (int64_t)kMaxBlockTargets * 148);
+    int64_t B = ceil_div(num_nodes, waves * 148);
+    B = (B + 7) / 8 * 8;
+    if (B < 8) B = 8;
+    if (B > kMaxBlockTargets) B = kMaxBlockTargets;
+    return (int)B;
+}
+
+int pack_weights(int nprod, int num_types, int K, int use_target, const float *const *weights, void *packed, int32_t *status,
+                 cudaStream_t st) {
+    WeightSrc src{};
+    for (int t = 0; t < num_types; ++t) src.w[t] = weights[t];
+    const int nseg = use_target ? 2 : 1;
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        if (nprod == 3) pack_weights_kernel<3><<<148, 256, 0, st>>>(src, num_types, K, nseg, static_cast<uint4 *>(packed), status);
+        else pack_weights_kernel<1><<<148, 256, 0, st>>>(src, num_types, K, nseg, static_cast<uint4 *>(packed), status);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+int pack_states(const float *h, int64_t rows, int K, void *packed, int32_t *status, cudaStream_t st) {
+    if (rows <= 0) return PTGNN_OK;
+    const int64_t items = rows * (K / 8);
+    const unsigned grid = (unsigned)(ceil_div(items, 256) < 148 * 8 ? ceil_div(items, 256) : 148 * 8);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_states_kernel<<<grid, 256, 0, st>>>(h, (long long)rows, K, static_cast<uint4 *>(packed), status);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+template <int NPROD, int K, int NSEG, int RED>
+static int launch_one(const Params &p, cudaStream_t st) {
+    auto kernel = fused_aggregate_kernel<NPROD, K, NSEG, RED>;
+    const int smem = smem_bytes(p.B);
+    // per launch, not once per process: the attribute belongs to the current device's context
+    PTGNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;
+    const int grid = p.num_blocks < sms ? p.num_blocks : sms;
+    {
+        TimedScope timed__(PTGNN_KERNEL_MESSAGE, st);
+        kernel<<<grid, NUM_THREADS, smem, st>>>(p);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+template <int NPROD, int K, int NSEG>
+static int launch_red(const Params &p, cudaStream_t st) {
+    switch (p.reduce) {
+        case PTGNN_REDUCE_SUM: return launch_one<NPROD, K, NSEG, PTGNN_REDUCE_SUM>(p, st);
+        case PTGNN_REDUCE_MEAN: return launch_one<NPROD, K, NSEG, PTGNN_REDUCE_MEAN>(p, st);
+        case PTGNN_REDUCE_MAX: return launch_one<NPROD, K, NSEG, PTGNN_REDUCE_MAX>(p, st);
+        default: return launch_one<NPROD, K, NSEG, PTGNN_REDUCE_MIN>(p, st);
+    }
+}
+template <int NPROD, int K>
+static int launch_seg(const Params &p, int use_target, cudaStream_t st) {
+    return use_target ? launch_red<NPROD, K, 2>(p, st) : launch_red<NPROD, K, 1>(p, st);
+}
+
+int aggregate(const AggregateArgs &a, cudaStream_t st) {
+    PTGNN_CHECK_ARG(supported(a.nprod, a.K, kD, a.use_target), "fused aggregate: unsupported nprod=%d K=%d", a.nprod, a.K);
+    PTGNN_CHECK_ARG(a.block_targets >= 8 && a.block_targets <= kMaxBlockTargets, "fused aggregate: block_targets=%d out of [8, %d]",
+                    a.block_targets, kMaxBlockTargets);
+    PTGNN_CHECK_ARG(a.num_types > 0 && a.num_types <= PTGNN_MAX_EDGE_TYPES, "fused aggregate: bad num_types=%d", a.num_types);
+    PTGNN_CHECK_ARG(a.reduce >= PTGNN_REDUCE_SUM && a.reduce <= PTGNN_REDUCE_MIN, "fused aggregate: bad reduce %d", a.reduce);
+    if (a.num_nodes <= 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(a.src_rows && a.group_off && a.packed_weights && a.out, "fused aggregate: null pointer");
+    PTGNN_CHECK_ARG(!a.use_target || a.tgt_rows, "fused aggregate: null target rows");
+    PTGNN_CHECK_ARG(a.reduce != PTGNN_REDUCE_MEAN || a.row_ptr, "fused aggregate: mean needs row_ptr");
+    Params p{};
+    p.src_rows = static_cast<const unsigned char *>(a.src_rows);
+    p.tgt_rows = static_cast<const unsigned char *>(a.tgt_rows);
+    p.wpack = static_cast<const uint4 *>(a.packed_weights);
+    p.group_off = a.group_off; p.src_f = a.src_f; p.tl_f = a.tl_f; p.row_ptr = a.row_ptr;
+    p.out = a.out; p.num_nodes = (int)a.num_nodes; p.B = a.block_targets;
+    p.num_blocks = (int)ceil_div(a.num_nodes, a.block_targets);
+    p.T = a.num_types; p.reduce = a.reduce; p.out_bf16 = a.out_bf16; p.epi = a.epi;
+    if (a.nprod == 3) {
+        if (a.K == 64) return launch_seg<3, 64>(p, a.use_target, st);
+        return launch_seg<3, 128>(p, a.use_target, st);
+    }
+    if (a.K == 64) return launch_seg<1, 64>(p, a.use_target, st);
+    if (a.K == 128) return launch_seg<1, 128>(p, a.use_target, st);
+    return launch_seg<1, 256>(p, a.use_target, st);
+}
+
+}  // namespace fused
+}  // namespace ptgnn

@@ -240,12 +240,6 @@ __global__ void __launch_bounds__(256) finalize_plan_kernel(const __grid_constan
     }
 }
 
-static int num_radix_passes(int64_t num_nodes) {
-    int bits = 1;
-    while (bits < 31 && ((int64_t)1 << bits) < num_nodes) ++bits;
-    return (bits + RADIX_BITS - 1) / RADIX_BITS;
-}
-
 struct PlanWs {
     size_t deg, scan_sums, keys_a, keys_b, vals_a, vals_b, hist, hist_sums, total;
 };
@@ -266,16 +260,17 @@ static PlanWs plan_ws_layout(int64_t N, int64_t E) {
     return w;
 }
 
-// Sorts (tgt32, edge id) stably by target into `perm`.  tgt32 is not modified.
-static int sort_edges_by_target(const int32_t *tgt32, int64_t N, int64_t E, int32_t *perm, char *ws, const PlanWs &L,
-                                cudaStream_t st) {
+// Stable LSD radix sort of (keys, edge id) over the low `key_bits` bits into `perm`; `keys` is not modified.  If
+// `sorted_keys` != nullptr it receives a pointer to the sorted key array (one of the workspace buffers).
+static int sort_edges_by_key(const int32_t *keys_in, int key_bits, int64_t E, int32_t *perm, char *ws, const PlanWs &L,
+                             cudaStream_t st, const int32_t **sorted_keys = nullptr) {
     const int64_t nblk = ceil_div(E, SORT_CHUNK);
     int32_t *keys[2] = {reinterpret_cast<int32_t *>(ws + L.keys_a), reinterpret_cast<int32_t *>(ws + L.keys_b)};
     int32_t *vals[2] = {reinterpret_cast<int32_t *>(ws + L.vals_a), reinterpret_cast<int32_t *>(ws + L.vals_b)};
     int32_t *hist = reinterpret_cast<int32_t *>(ws + L.hist);
     int32_t *hist_sums = reinterpret_cast<int32_t *>(ws + L.hist_sums);
-    const int passes = num_radix_passes(N);
-    const int32_t *kin = tgt32;
+    const int passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
+    const int32_t *kin = keys_in;
     const int32_t *vin = nullptr;
     for (int p = 0; p < passes; ++p) {
         int32_t *kout = keys[p & 1];
@@ -296,7 +291,56 @@ static int sort_edges_by_target(const int32_t *tgt32, int64_t N, int64_t E, int3
         kin = kout;
         vin = vout;
     }
+    if (sorted_keys) *sorted_keys = kin;
     return PTGNN_OK;
+}
+static int bits_for(int64_t n) {
+    int bits = 1;
+    while (bits < 31 && ((int64_t)1 << bits) < n) ++bits;
+    return bits;
+}
+// Sorts (tgt32, edge id) stably by target into `perm`.  tgt32 is not modified.
+static int sort_edges_by_target(const int32_t *tgt32, int64_t N, int64_t E, int32_t *perm, char *ws, const PlanWs &L,
+                                cudaStream_t st) {
+    return sort_edges_by_key(tgt32, bits_for(N), E, perm, ws, L, st);
+}
+
+// =================================================================================================
+// block plan for the fused gather -> Linear -> reduce kernel (fused_mp.cu): edges sorted, stably, by
+// (target block, edge type, target).  key = block << 16 | type << 8 | (target - block * B);  B <= 256, types <= 128.
+// =================================================================================================
+__global__ void __launch_bounds__(256) block_keys_kernel(const __grid_constant__ TypeOffsets toff, int64_t num_edges,
+                                                         const int32_t *__restrict__ tgt32, int B, int32_t *__restrict__ keys,
+                                                         int32_t *__restrict__ group_count) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += (int64_t)gridDim.x * blockDim.x) {
+        const int t = type_of_edge(toff.off, toff.num_types, e);
+        const int v = tgt32[e];
+        const int blk = v / B, tl = v - blk * B;
+        keys[e] = (blk << 16) | (t << 8) | tl;
+        atomicAdd(&group_count[(int64_t)blk * toff.num_types + t], 1);
+    }
+}
+__global__ void __launch_bounds__(256) block_finalize_kernel(int64_t num_edges, const int32_t *__restrict__ perm,
+                                                             const int32_t *__restrict__ sorted_keys,
+                                                             const int32_t *__restrict__ src32, int32_t *__restrict__ src_f,
+                                                             uint8_t *__restrict__ tl_f) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < num_edges; j += (int64_t)gridDim.x * blockDim.x) {
+        src_f[j] = src32[perm[j]];
+        tl_f[j] = (uint8_t)(sorted_keys[j] & 0xFF);
+    }
+}
+struct BlockPlanWs { size_t keys, perm, scan_sums, plan, total; };
+static BlockPlanWs block_plan_ws_layout(int64_t N, int64_t E, int T, int B) {
+    BlockPlanWs w{};
+    const int64_t nblk = ceil_div(N > 0 ? N : 1, B), groups = nblk * (T > 0 ? T : 1) + 1;
+    size_t o = 0;
+    auto add = [&](size_t cnt) { size_t at = o; o += ws_slice(cnt, 4); return at; };
+    w.keys = add((size_t)E + 1);
+    w.perm = add((size_t)E + 1);
+    w.scan_sums = add(scan_workspace_elems(groups));
+    w.plan = o; o += plan_ws_layout(N, E).total;
+    w.total = o;
+    return w;
 }
 
 }  // namespace ptgnn
@@ -370,6 +414,58 @@ extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes
     {
         TimedScope timed__(PTGNN_KERNEL_PLAN, st);
         finalize_plan_kernel<<<grid, 256, 0, st>>>(toff, E, perm, src32, pos, src_sorted, etype_sorted);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+extern "C" size_t ptgnn_b200_block_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types,
+                                                        int32_t block_targets) {
+    if (num_nodes < 0 || num_edges < 0 || num_types < 0 || block_targets <= 0) return 0;
+    return block_plan_ws_layout(num_nodes, num_edges, num_types, block_targets).total;
+}
+
+extern "C" int ptgnn_b200_block_plan_build(int64_t num_nodes, int32_t num_types, const int64_t *type_off,
+                                           const int32_t *src32, const int32_t *tgt32, int32_t block_targets,
+                                           int32_t *group_off, int32_t *src_f, uint8_t *tl_f, void *workspace,
+                                           size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = block_targets, T = num_types;
+    PTGNN_CHECK_ARG(num_nodes >= 0 && num_nodes < INT32_MAX, "block_plan_build: num_nodes out of range");
+    PTGNN_CHECK_ARG(T > 0 && T <= PTGNN_MAX_EDGE_TYPES && type_off, "block_plan_build: bad num_types=%d", T);
+    PTGNN_CHECK_ARG(B >= 8 && B <= 256, "block_plan_build: block_targets=%d must be in [8, 256]", B);
+    const int64_t E = type_off[T];
+    PTGNN_CHECK_ARG(E >= 0 && E < INT32_MAX, "block_plan_build: edge count out of range");
+    const int64_t nblk = ceil_div(num_nodes, B), groups = nblk * T;
+    PTGNN_CHECK_ARG(nblk < (1 << 15), "block_plan_build: %lld target blocks do not fit the 15-bit key field", (long long)nblk);
+    PTGNN_CHECK_ARG(group_off, "block_plan_build: null group_off");
+    const BlockPlanWs L = block_plan_ws_layout(num_nodes, E, T, B);
+    if (workspace_bytes < L.total || !workspace) {
+        set_error("block_plan_build: workspace %zu < required %zu", workspace_bytes, L.total);
+        return PTGNN_E_WORKSPACE;
+    }
+    PTGNN_CUDA(cudaMemsetAsync(group_off, 0, sizeof(int32_t) * (size_t)(groups + 1), st));
+    if (E == 0 || num_nodes == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(src32 && tgt32 && src_f && tl_f, "block_plan_build: null edge array");
+    char *ws = static_cast<char *>(workspace);
+    int32_t *keys = reinterpret_cast<int32_t *>(ws + L.keys), *perm = reinterpret_cast<int32_t *>(ws + L.perm);
+    TypeOffsets toff{};
+    toff.num_types = T;
+    for (int t = 0; t <= PTGNN_MAX_EDGE_TYPES; ++t) toff.off[t] = (int32_t)type_off[t < T ? t : T];
+    const unsigned grid = (unsigned)(ceil_div(E, 256) < 148 * 16 ? ceil_div(E, 256) : 148 * 16);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        block_keys_kernel<<<grid, 256, 0, st>>>(toff, E, tgt32, B, keys, group_off);
+    }
+    PTGNN_LAUNCHED();
+    int rc = exclusive_scan_i32(group_off, group_off, groups + 1, reinterpret_cast<int32_t *>(ws + L.scan_sums), nullptr, st);
+    if (rc) return rc;
+    const int32_t *sorted_keys = nullptr;
+    rc = sort_edges_by_key(keys, 16 + bits_for(nblk), E, perm, ws + L.plan, plan_ws_layout(num_nodes, E), st, &sorted_keys);
+    if (rc) return rc;
+    {
+        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+        block_finalize_kernel<<<grid, 256, 0, st>>>(E, perm, sorted_keys, src32, src_f, tl_f);
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;

@@ -123,8 +123,8 @@ extern "C" size_t ptgnn_b200_scatter_workspace_bytes(int64_t num_nodes, int64_t 
 }
 
 extern "C" int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, int64_t num_edges, int32_t dim,
-                                      int64_t num_nodes, int32_t reduce, float *out, int64_t *arg_out, void *workspace,
-                                      size_t workspace_bytes, void *stream) {
+                                      int64_t num_nodes, int32_t reduce, float *out, int64_t *arg_out, int32_t *status,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
     const ScatterWs L = scatter_ws_layout(num_nodes, num_edges);
     if (workspace_bytes < L.total || !workspace) {
         set_error("scatter: workspace %zu < required %zu", workspace_bytes, L.total);
@@ -137,7 +137,7 @@ extern "C" int ptgnn_b200_scatter_f32(const float *src, const int64_t *index, in
     const int64_t counts[1] = {num_edges};
     int rc = ptgnn_b200_plan_build(num_nodes, num_nodes, 1, ptrs, ptrs, counts, p32(L.row_ptr), p32(L.perm), p32(L.pos),
                                    p32(L.src_sorted), reinterpret_cast<uint8_t *>(ws + L.etype_sorted), p32(L.src32),
-                                   p32(L.tgt32), p32(L.status), ws + L.plan, workspace_bytes - L.plan, stream);
+                                   p32(L.tgt32), status ? status : p32(L.status), ws + L.plan, workspace_bytes - L.plan, stream);
     if (rc) return rc;
     return launch_segment_reduce(src, p32(L.row_ptr), p32(L.perm), num_nodes, num_edges, dim, reduce, out, arg_out,
                                  nullptr, static_cast<cudaStream_t>(stream));

@@ -7,6 +7,7 @@ The reference re-derives the same information inside every layer call: it concat
 (``ptgnn_b200_plan_build``: int64->int32, degree histogram, scan, stable radix sort by target) and reused by all
 L layers (the reference's weight-shared stacks call the same layer 7-8 times on the same adjacency).
 """
+import threading
 from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple
 
@@ -22,8 +23,13 @@ class EdgePlan:
 
     __slots__ = (
         "num_nodes", "num_source_nodes", "num_edges", "num_types", "type_off", "type_off_c", "row_ptr", "perm", "pos", "src_sorted",
-        "etype_sorted", "src32", "tgt32", "status", "device", "_keepalive", "_validated",
+        "etype_sorted", "src32", "tgt32", "status", "device", "_keepalive", "_validated", "_block",
     )
+
+    # status words (pinned host memory the kernels write directly, so the host can poll them without synchronising):
+    # [0] number of out-of-range edge indices, [1] a node state / [2] an edge weight outside the fp16 range of the fp32-exact
+    # fused path (csrc/fused_mp.cuh)
+    STATUS_WORDS = 4
 
     def __init__(self, adjacency_lists: Adjacency, num_nodes: int, validate: bool = False,
                  num_source_nodes: Optional[int] = None):
@@ -54,7 +60,8 @@ class EdgePlan:
         self.row_ptr = i32(num_nodes + 1)
         self.perm, self.pos, self.src_sorted, self.src32, self.tgt32 = i32(E), i32(E), i32(E), i32(E), i32(E)
         self.etype_sorted = torch.empty(E, dtype=torch.uint8, device=device)
-        self.status = i32(1)
+        self.status = torch.zeros(self.STATUS_WORDS, dtype=torch.int32).pin_memory()
+        self._block = None
         lib = N.lib()
         ws_bytes = lib.ptgnn_b200_plan_workspace_bytes(num_nodes, E)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=device)
@@ -71,12 +78,51 @@ class EdgePlan:
             self.validate()
 
     def validate(self) -> None:
-        """Synchronises and raises IndexError if any edge index was outside [0, num_nodes)."""
+        """Synchronises the current stream and raises if the plan or a layer that used it reported an error."""
         if not self._validated:
-            bad = int(self.status.item())
-            if bad:
-                raise IndexError(f"{bad} edge indices outside [0, {self.num_nodes}) (targets) / [0, {self.num_source_nodes}) (sources)")
+            torch.cuda.current_stream(self.device).synchronize()
+            self.poll()
             self._validated = True
+
+    def poll(self) -> None:
+        """Host-side look at the status words, WITHOUT synchronising: errors of work that has already executed are raised
+        here (every layer call and plan lookup polls), errors of work still in flight at the next poll or `validate()`.
+        The reference fails in the same situations (IndexError from F.embedding / a device assert from scatter)."""
+        st = self.status
+        if int(st[0]):
+            raise IndexError(f"{int(st[0])} edge indices outside [0, {self.num_nodes}) (targets) / [0, {self.num_source_nodes}) "
+                             "(sources); the kernels route such edges to node 0, results are not valid")
+        if int(st[1]) or int(st[2]):
+            what = "node states" if int(st[1]) else "edge weights"
+            raise FloatingPointError(
+                f"{what} outside the fp16 range (|x| >= 65504, inf or NaN) reached the fp32-exact fused kernel (3xFP16 split); "
+                "set PTGNN_B200_FP32_MODE=tf32 to use the unfused 3xTF32 kernels for such inputs")
+
+    # ---- block plan of the fused kernel (built on first use, shared by all layers of the minibatch) ---------------------
+    def block_plan(self) -> "N.BlockPlanStruct":
+        if self._block is None:
+            lib = N.lib()
+            B = int(lib.ptgnn_b200_block_plan_block_targets(self.num_nodes))
+            nblk = (self.num_nodes + B - 1) // B
+            dev = self.device
+            group_off = torch.empty(nblk * self.num_types + 1, dtype=torch.int32, device=dev)
+            src_f = torch.empty(max(self.num_edges, 1), dtype=torch.int32, device=dev)
+            tl_f = torch.empty(max(self.num_edges, 1), dtype=torch.uint8, device=dev)
+            ws_bytes = lib.ptgnn_b200_block_plan_workspace_bytes(self.num_nodes, self.num_edges, self.num_types, B)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.ptgnn_b200_block_plan_build(self.num_nodes, self.num_types, self.type_off_c, N.ptr(self.src32), N.ptr(self.tgt32),
+                                                     B, N.ptr(group_off), N.ptr(src_f), N.ptr(tl_f), N.ptr(ws), ws_bytes,
+                                                     N.current_stream(dev))
+            N.check(rc, "ptgnn_b200_block_plan_build")
+            struct = N.BlockPlanStruct(B, N.ptr(group_off), N.ptr(src_f), N.ptr(tl_f), self.status.data_ptr() + 4)
+            self._block = (struct, group_off, src_f, tl_f, B)
+        return self._block[0]
+
+    @property
+    def block_targets(self) -> int:
+        self.block_plan()
+        return self._block[4]
 
 
 # ---- small identity-keyed cache so that the L layers of one forward share one plan ----------------
@@ -84,29 +130,72 @@ _CACHE: "OrderedDict[tuple, EdgePlan]" = OrderedDict()
 _CACHE_SIZE = 4
 
 
+def _version(t: torch.Tensor):
+    try:
+        return t._version
+    except RuntimeError:       # inference tensors carry no version counter: a sentinel that never compares equal
+        return object()
+
+
 def _key(adjacency_lists: Adjacency, num_nodes: int, num_source_nodes: Optional[int] = None) -> tuple:
-    parts: List[int] = [num_nodes, -1 if num_source_nodes is None else num_source_nodes]
+    parts: list = [num_nodes, -1 if num_source_nodes is None else num_source_nodes]
     for s, t in adjacency_lists:
-        parts += [s.data_ptr(), s.shape[0], s._version, t.data_ptr(), t._version]
+        parts += [s.data_ptr(), s.shape[0], _version(s), t.data_ptr(), _version(t)]
     return tuple(parts)
+
+
+# ---- plan hand-off from a container to its layers: per thread, never process-global ---------------------------------------
+_TLS = threading.local()
+
+
+def current_shared_plan() -> Optional[EdgePlan]:
+    return getattr(_TLS, "plan", None)
+
+
+class shared_plan:
+    """`with shared_plan(plan):` -- layers called inside (on this thread) use `plan` if it matches their adjacency lists'
+    edge / node counts; nests; other threads are unaffected (the reference builds minibatches on background threads)."""
+
+    def __init__(self, plan: Optional[EdgePlan]):
+        self.plan, self.previous = plan, None
+
+    def __enter__(self):
+        self.previous = getattr(_TLS, "plan", None)
+        _TLS.plan = self.plan
+        return self.plan
+
+    def __exit__(self, *exc):
+        _TLS.plan = self.previous
+        return False
 
 
 def plan_for(adjacency_lists: Adjacency, num_nodes: int, plan: Optional[EdgePlan] = None,
              num_source_nodes: Optional[int] = None) -> EdgePlan:
     """Returns the plan for these adjacency tensors, building it on a cache miss.  Entries keep their index tensors
     alive, so a (data_ptr, version) key cannot alias different contents."""
-    if plan is not None:
+    if plan is not None and _matches(plan, adjacency_lists, num_nodes, num_source_nodes):
+        plan.poll()
         return plan
     key = _key(adjacency_lists, num_nodes, num_source_nodes)
     hit = _CACHE.get(key)
     if hit is not None:
         _CACHE.move_to_end(key)
+        hit.poll()
         return hit
     built = EdgePlan(adjacency_lists, num_nodes, num_source_nodes=num_source_nodes)
     _CACHE[key] = built
     while len(_CACHE) > _CACHE_SIZE:
         _CACHE.popitem(last=False)
     return built
+
+
+def _matches(plan: EdgePlan, adjacency_lists: Adjacency, num_nodes: int, num_source_nodes: Optional[int]) -> bool:
+    """A handed-over plan is only used for the call it was built for (same node / edge / type counts per type)."""
+    if plan.num_nodes != num_nodes or plan.num_types != len(adjacency_lists):
+        return False
+    if num_source_nodes is not None and plan.num_source_nodes != num_source_nodes:
+        return False
+    return all(plan.type_off[i + 1] - plan.type_off[i] == int(s.shape[0]) for i, (s, _) in enumerate(adjacency_lists))
 
 
 def clear_plan_cache() -> None:

@@ -11,7 +11,7 @@ from typing import Any, Dict, List, NamedTuple, Optional, Tuple
 import torch
 from torch import nn
 
-from .edgeplan import EdgePlan, plan_for
+from .edgeplan import EdgePlan, plan_for, shared_plan
 from .messagepassing import AbstractMessagePassingLayer
 
 
@@ -111,10 +111,8 @@ class GraphNeuralNetwork(nn.Module):
             raise NotImplementedError("training-mode edge dropout has no native kernel (forward-only round)")
         if node_representations.is_cuda:
             plan = plan_for(adjacency_lists, node_representations.shape[0], plan)
-        previous = AbstractMessagePassingLayer._shared_plan
-        AbstractMessagePassingLayer._shared_plan = plan
-        try:
-            all_states = [node_representations]
+        all_states = [node_representations]
+        with shared_plan(plan):     # per-thread hand-off: the layers of this call (and only they) reuse the plan
             for layer in self.__message_passing_layers:
                 node_representations = layer(
                     node_states=node_representations,
@@ -125,8 +123,6 @@ class GraphNeuralNetwork(nn.Module):
                     edge_features=edge_feature_embeddings,
                 )
                 all_states.append(node_representations)
-        finally:
-            AbstractMessagePassingLayer._shared_plan = previous
         if return_all_states:
             node_representations = torch.cat(all_states, dim=-1)
         return node_representations

@@ -20,8 +20,11 @@ from typing import Dict, List, Optional, Tuple, Union
 import torch
 from torch import nn
 
+import ctypes
+import os
+
 from . import _native as N
-from .edgeplan import EdgePlan, plan_for
+from .edgeplan import EdgePlan, current_shared_plan, plan_for
 
 _ACTIVATION_CODES = {type(None): N.ACT_NONE, nn.GELU: N.ACT_GELU, nn.Tanh: N.ACT_TANH, nn.ReLU: N.ACT_RELU}
 
@@ -47,6 +50,29 @@ def _refuse_autograd(module: nn.Module, node_states: torch.Tensor) -> None:
         )
 
 
+def _fused_enabled() -> bool:
+    """The fused gather -> Linear -> reduce kernel is the default wherever it supports the dimensions.  PTGNN_B200_FUSED=0
+    selects the round-1 three-kernel path; PTGNN_B200_FP32_MODE=tf32 does so for fp32 states only (3xTF32 instead of 3xFP16:
+    needed for states / weights beyond the fp16 range)."""
+    return os.environ.get("PTGNN_B200_FUSED", "1") != "0"
+
+
+def _use_fused(lib, bf16: bool, H: int, D: int) -> bool:
+    if not _fused_enabled() or (not bf16 and os.environ.get("PTGNN_B200_FP32_MODE", "") == "tf32"):
+        return False
+    return bool(lib.ptgnn_b200_fused_supported(int(bf16), H, D))
+
+
+def _check_states(node_states: torch.Tensor, expected_dim: int, what: str) -> None:
+    if node_states.dim() != 2 or node_states.shape[1] != expected_dim:
+        raise ValueError(f"{what}: node_states must be [num_nodes, {expected_dim}], got {tuple(node_states.shape)}")
+
+
+def _check_shape(t: torch.Tensor, shape: Tuple[int, ...], name: str) -> None:
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
 def _check_no_edge_features(edge_features: Optional[List[torch.Tensor]]) -> None:
     for f in edge_features or []:
         if f is not None and f.dim() == 2 and f.shape[1] != 0:
@@ -55,10 +81,6 @@ def _check_no_edge_features(edge_features: Optional[List[torch.Tensor]]) -> None
 
 class AbstractMessagePassingLayer(nn.Module):
     """Interface of a message passing layer over multiple edge types (same contract as the reference's)."""
-
-    # A plan prepared by the container for the current minibatch (GraphNeuralNetwork.gnn sets/clears it);
-    # when absent the layer finds or builds the plan itself through the identity-keyed cache.
-    _shared_plan: Optional[EdgePlan] = None
 
     @abstractmethod
     def forward(
@@ -81,7 +103,15 @@ class AbstractMessagePassingLayer(nn.Module):
         )
 
     def _plan(self, adjacency_lists, num_nodes: int, num_source_nodes: Optional[int] = None) -> EdgePlan:
-        return plan_for(adjacency_lists, num_nodes, AbstractMessagePassingLayer._shared_plan, num_source_nodes)
+        """The plan a container prepared for this minibatch on this thread (`edgeplan.shared_plan`) if it matches the call,
+        else the identity-keyed cache / a fresh build."""
+        return plan_for(adjacency_lists, num_nodes, current_shared_plan(), num_source_nodes)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float(): device copies of the parameters derived for the old placement are dead
+        if hasattr(self, "_derived_weights"):
+            self._derived_weights = {}
+        return super()._apply(fn, *args, **kwargs)
 
     @staticmethod
     def _gather_source(gather_states: Optional[torch.Tensor], h: torch.Tensor) -> Optional[torch.Tensor]:
@@ -172,6 +202,7 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         reduce = _reduce_code(self.__aggregation_fn)
 
         state_dtype = node_states.dtype if node_states.dtype == torch.bfloat16 else torch.float32
+        _check_states(node_states, self.__state_dimension, "GatedMessagePassingLayer")
         h = N.require_cuda(node_states, "node_states", state_dtype)
         num_nodes, H = h.shape
         D = self.__message_dimension
@@ -183,9 +214,32 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         weights = [N.require_cuda(lin.weight, "edge weight", torch.float32) for lin in linears]
         w_ih, w_hh = N.require_cuda(gru.weight_ih, "weight_ih", torch.float32), N.require_cuda(gru.weight_hh, "weight_hh", torch.float32)
         b_ih, b_hh = N.require_cuda(gru.bias_ih, "bias_ih", torch.float32), N.require_cuda(gru.bias_hh, "bias_hh", torch.float32)
+        for i, w in enumerate(weights):      # raw pointers cross the C ABI next: the shapes must be what the kernels assume
+            _check_shape(w, (D, H), f"edge weight {i}")
+        _check_shape(w_ih, (3 * H, D), "GRUCell.weight_ih"); _check_shape(w_hh, (3 * H, H), "GRUCell.weight_hh")
+        _check_shape(b_ih, (3 * H,), "GRUCell.bias_ih"); _check_shape(b_hh, (3 * H,), "GRUCell.bias_hh")
 
         lib = N.lib()
         params = weights + [w_ih, w_hh, b_ih, b_hh]
+        bf16 = state_dtype == torch.bfloat16
+        if plan.num_edges > 0 and _use_fused(lib, bf16, H, D):
+            # gather -> W_t -> segmented reduce in ONE kernel (no [E, D] message tensor), then the GRUCell kernel
+            kind = "bf16_fused" if bf16 else "f32_fused"
+            cache, valid = self._weight_cache(kind, lib.ptgnn_b200_gated_fused_weight_cache_bytes(int(bf16), plan.num_types, H, D), params, h.device)
+            ns = num_nodes if gsrc is None else gsrc.shape[0]
+            ws_bytes = lib.ptgnn_b200_gated_fused_workspace_bytes(int(bf16), num_nodes, ns, plan.num_types, H, D)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
+            out = torch.empty_like(h)
+            bp = plan.block_plan()
+            with torch.cuda.device(h.device):
+                rc = lib.ptgnn_b200_gated_forward_fused(
+                    int(bf16), N.ptr(h), N.ptr(gsrc), num_nodes, ns, H, D, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
+                    N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce, N.ptr(out), N.ptr(ws), ws_bytes,
+                    N.ptr(cache), 0 if cache is None else cache.numel(), int(valid), N.current_stream(h.device),
+                )
+            N.check(rc, "ptgnn_b200_gated_forward_fused")
+            self._weight_cache_filled(kind, h.device)
+            return out
         if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
             cache, valid = self._weight_cache("bf16", lib.ptgnn_b200_gated_weight_cache_bytes_bf16(plan.num_types, H, D), params, h.device)
             ws_bytes = lib.ptgnn_b200_gated_workspace_bytes_bf16(num_nodes, plan.num_edges, plan.num_types, H, D)
@@ -396,6 +450,7 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
                 dense_act = _activation_code(m, "dense_activation")
 
         state_dtype = node_states.dtype if node_states.dtype == torch.bfloat16 else torch.float32
+        _check_states(node_states, self.__input_state_dim, "MlpMessagePassingLayer")
         h = N.require_cuda(node_states, "node_states", state_dtype)
         num_nodes, H = h.shape
         D = self.__message_dim
@@ -407,8 +462,30 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
         ln_w, ln_b = (f32(ln.weight, "ln.weight"), f32(ln.bias, "ln.bias")) if ln is not None else (None, None)
         d_w = f32(dense.weight, "dense.weight") if dense is not None else None
         d_b = f32(dense.bias, "dense.bias") if dense is not None and dense.bias is not None else None
+        ut_i = int(self.__use_target_state_as_message_input)
+        for i, w in enumerate(weights):
+            _check_shape(w, (D, (1 + ut_i) * H), f"edge weight {i}")
+        if ln_w is not None:
+            _check_shape(ln_w, (D,), "LayerNorm.weight"); _check_shape(ln_b, (D,), "LayerNorm.bias")
+        if d_w is not None:
+            _check_shape(d_w, (out_dim, D), "dense.weight")
 
         lib = N.lib()
+        bf16 = state_dtype == torch.bfloat16
+        if plan.num_edges > 0 and _use_fused(lib, bf16, H, D):
+            ns = num_nodes if gsrc is None else gsrc.shape[0]
+            ws_bytes = lib.ptgnn_b200_mlp_fused_workspace_bytes(int(bf16), num_nodes, ns, plan.num_types, H, D, out_dim, ut_i)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
+            out = torch.empty(num_nodes, out_dim, dtype=state_dtype, device=h.device)
+            bp = plan.block_plan()
+            with torch.cuda.device(h.device):
+                rc = lib.ptgnn_b200_mlp_forward_fused(
+                    int(bf16), N.ptr(h), N.ptr(gsrc), num_nodes, ns, H, D, out_dim, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
+                    N.ptr_table(weights), ut_i, reduce, msg_act, N.ptr(ln_w), N.ptr(ln_b), float(ln.eps) if ln is not None else 0.0,
+                    N.ptr(d_w), N.ptr(d_b), dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+                )
+            N.check(rc, "ptgnn_b200_mlp_forward_fused")
+            return out
         if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
             ut = int(self.__use_target_state_as_message_input)
             ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes_bf16(num_nodes, plan.num_edges, plan.num_types, H, D, out_dim, ut)

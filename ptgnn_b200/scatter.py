@@ -28,11 +28,37 @@ def _run(src: torch.Tensor, index: torch.Tensor, dim: int, dim_size: Optional[in
     arg = torch.empty(dim_size, D, dtype=torch.int64, device=src.device) if want_arg else None
     ws_bytes = lib.ptgnn_b200_scatter_workspace_bytes(dim_size, E)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=src.device)
+    _poll_status()
+    status = torch.zeros(1, dtype=torch.int32).pin_memory()     # written by the kernels, polled without synchronising
     with torch.cuda.device(src.device):
         rc = lib.ptgnn_b200_scatter_f32(N.ptr(src), N.ptr(index), E, D, dim_size, N.REDUCE[reduce], N.ptr(out), N.ptr(arg),
-                                        N.ptr(ws), ws_bytes, N.current_stream(src.device))
+                                        status.data_ptr(), N.ptr(ws), ws_bytes, N.current_stream(src.device))
     N.check(rc, "ptgnn_b200_scatter_f32")
+    _PENDING.append((status, dim_size))
     return out, arg
+
+
+# Out-of-range indices are reported by the kernels through a pinned status word; the reference (torch_scatter) raises an
+# IndexError / device assert in that case.  Checked without synchronising: at the next scatter call, or by check_scatter_status().
+_PENDING: list = []
+
+
+def _poll_status() -> None:
+    keep = []
+    try:
+        for status, n in _PENDING:
+            bad = int(status[0])
+            if bad:
+                raise IndexError(f"scatter: {bad} indices outside [0, {n}); such rows were routed to row 0, the result is not valid")
+        keep = _PENDING[-8:]
+    finally:
+        _PENDING[:] = keep
+
+
+def check_scatter_status(device=None) -> None:
+    """Synchronises and raises IndexError if any scatter call issued so far saw an out-of-range index."""
+    torch.cuda.synchronize(device)
+    _poll_status()
 
 
 def scatter(src, index, dim: int = -1, out=None, dim_size: Optional[int] = None, reduce: str = "sum") -> torch.Tensor:

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/ptgnn_b200.h but not exported"
     assert sorted(N.SIGNATURES) == declared, "ctypes SIGNATURES must cover exactly the header's entry points"
-    assert handle.ptgnn_b200_abi_version() == 1
+    assert handle.ptgnn_b200_abi_version() == 2
 
 
 def test_workspace_size_queries_run_without_a_gpu():
