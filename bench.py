@@ -42,16 +42,27 @@ def measured_peaks():
 
 
 def measured_tensor_peak():
+    """(TFLOP/s, which).  The per-kernel numbers come from a timed region of ~0.1 s at full clocks (see `clocks` in the line), so the
+    BURST cuBLAS bf16 figure is the honest denominator here -- the sustained one was measured at a 1372 MHz power-capped median
+    ("burst is the right one here")."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["bf16_tflops_sustained"])
-    return 1400.0
+            return float(json.load(f)["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst cuBLAS bf16; the timed region is ~0.1 s at full clocks)"
+    return 1590.0, "fallback 1.59 PFLOP/s burst (B200_PROFILING.md)"
 
 
-# DRAM traffic per launch (read + write bytes) of the kernels from the committed ncu --set full capture
-# (profiles/r01_final_*.md); None when no capture of the current kernel exists.
-NCU_TRAFFIC = {"message": 945.1e6, "reduce": 621.0e6, "gru": 290.2e6}   # profiles/r01b_kernels_f32.md (config 2, sum)
+def ncu_traffic(dtype: str):
+    """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the CURRENT kernels, from the committed ncu
+    --set full capture: profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic from the .ncu-rep of the round.
+    Empty when no capture of this dtype's kernels is committed (traffic is then reported as null)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {k: float(v) for k, v in d.get(dtype, {}).get("kernels", {}).items()}, d.get(dtype, {}).get("source")
+    except (OSError, ValueError):
+        return {}, None
 
 
 def usable_cores() -> int:
@@ -294,7 +305,8 @@ def main():
                     f"{NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), {args.dtype}",
         "step": "edge-plan build + 8 layers on one minibatch",
         "parallelism": f"graph-sharded x{world} (no data-path collective)",
-        "l2": "per-layer working set ~0.8 GB (messages 566 MB + states) > 126 MB L2; no explicit flush",
+        "l2": "per-layer working set (states in + packed copy + aggregate + states out: 0.42 GB fp32 / 0.16 GB bf16) > 126 MB L2 and "
+              "every layer reads what the previous one wrote; no explicit flush",
     }
 
     # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
@@ -476,67 +488,87 @@ def main():
     kt = N.read_kernel_timing()
     N.kernel_timing(False)
     peak, peak_src = measured_peaks()
-    tensor_peak = measured_tensor_peak()
+    tensor_peak, tensor_src = measured_tensor_peak()
     D = HIDDEN
-    alg_bytes = {  # per launch, see DESIGN.md section 3 ("alg. bytes"); esz = bytes per state / message element
-        "message": n_nodes * HIDDEN * esz + E * (D * esz + 8),
-        "reduce": E * D * esz + (n_nodes + 1) * 4 + n_nodes * D * esz,
-        "gru": n_nodes * D * esz + 2 * n_nodes * HIDDEN * esz + 6 * HIDDEN * HIDDEN * esz,
-    }
-    alg_flops = {  # fp32 multiply-adds the reference performs (x2); the 3xTF32 path issues 3x this on the tensor cores
+    fused = kt.get("reduce", (0.0, 0))[1] == 0          # no stand-alone reduce launches: the fused aggregation kernel ran
+    w_bytes = T * D * HIDDEN * (4 if args.dtype == "f32" else 2)          # packed edge weights (hi|lo' fp16 pairs, or bf16)
+    if fused:
+        alg_bytes = {  # per launch: states once (per-graph working set is L2 resident), 5 index bytes per
+                       # edge + group offsets, weights, the aggregate written once -- there is no [E, D] tensor any more
+            "message": n_nodes * HIDDEN * esz + E * 5 + (n_nodes // 128 + 1) * T * 4 + w_bytes + n_nodes * D * esz,
+            "gru": n_nodes * D * esz + 2 * n_nodes * HIDDEN * esz + 6 * HIDDEN * HIDDEN * esz,
+            "pack": 2 * n_nodes * HIDDEN * 4,
+        }
+    else:
+        alg_bytes = {
+            "message": n_nodes * HIDDEN * esz + E * (D * esz + 8),
+            "reduce": E * D * esz + (n_nodes + 1) * 4 + n_nodes * D * esz,
+            "gru": n_nodes * D * esz + 2 * n_nodes * HIDDEN * esz + 6 * HIDDEN * HIDDEN * esz,
+        }
+    alg_flops = {  # the reference's multiply-adds (x2)
         "message": 2 * E * HIDDEN * D,
         "gru": 2 * n_nodes * (3 * HIDDEN * D + 3 * HIDDEN * HIDDEN),
     }
+    # MMAs issued per reference product and their rate relative to the bf16 peak: fused fp32 = 3 kind::f16 products (3xFP16);
+    # unfused fp32 message / GRU = 3 kind::tf32 products at half the bf16 rate (3xTF32); bf16 = 1
+    if args.dtype == "f32":
+        exact_div = {"message": 3.0 if fused else 6.0, "gru": 6.0}
+    else:
+        exact_div = {"message": 1.0, "gru": 1.0}
     kernel_names = {"message": "tc_pipeline_kernel<MsgPolicy> (edge messages)", "reduce": "segment_reduce_stream_kernel",
                     "gru": "tc_pipeline_kernel<GruPolicy> (GRUCell update)", "plan": "edge-plan kernels", "pack": "weight split/pack"}
     if args.dtype == "bf16":
         kernel_names.update(message="tc_pipeline_bf16_kernel<MsgPolicyB>", reduce="segment_reduce_bf16_kernel",
                             gru="tc_pipeline_bf16_kernel<GruPolicyB>")
+    if fused:
+        kernel_names.update(message="fused_aggregate_kernel (gather -> W_t -> segmented reduce, %s)" % ("3xFP16" if args.dtype == "f32" else "bf16"),
+                            pack="pack_states_kernel (fp32 -> fp16 hi|lo' rows) + weight packing", plan="edge-plan + block-plan kernels")
+    traffic, traffic_src = ncu_traffic(args.dtype)
     kernels = {}
     for name, (ms, cnt) in kt.items():
         if cnt:
             avg_ms = ms / cnt
             entry = {"kernel": kernel_names.get(name, name), "avg_ms": avg_ms, "launches_per_step": cnt / ksteps,
                      "share_of_step": ms / ksteps / ms_step}
-            if name in alg_bytes:
+            if name in alg_bytes and not (name == "pack" and args.dtype == "bf16"):
                 entry["alg_bytes"] = alg_bytes[name]
                 entry["achieved_gbs"] = alg_bytes[name] / (avg_ms * 1e-3) / 1e9
                 entry["frac_hbm"] = entry["achieved_gbs"] / peak
+                entry["ncu_dram_bytes"] = traffic.get(name)
             if name in alg_flops:
                 entry["alg_tflops"] = alg_flops[name] / (avg_ms * 1e-3) / 1e12
                 entry["frac_tensor_bf16_peak"] = entry["alg_tflops"] / tensor_peak
             kernels[name] = entry
     # Which roofline bounds a kernel: the larger of its HBM floor (algorithmic bytes / measured copy bandwidth) and its tensor
-    # floor.  fp32 results on the tensor cores need 3xTF32 (three kind::tf32 MMAs per product, tf32 dense rate = half the
-    # measured bf16 rate), so the fp32-exact ceiling in ALGORITHMIC flops is tensor_peak / 2 / 3; bf16 kernels use tensor_peak.
-    exact_peak = tensor_peak / 2.0 / 3.0 if args.dtype == "f32" else tensor_peak
+    # floor (algorithmic flops x MMAs per product / measured bf16 rate).
     for name, entry in kernels.items():
         if "alg_bytes" not in entry:
             continue
         t_hbm = entry["alg_bytes"] / (peak * 1e9)
-        t_tensor = alg_flops[name] / (exact_peak * 1e12) if name in alg_flops else 0.0
+        ceiling = tensor_peak / exact_div.get(name, 1.0)
+        t_tensor = alg_flops[name] / (ceiling * 1e12) if name in alg_flops else 0.0
         entry["floor_ms"] = {"hbm": t_hbm * 1e3, "tensor": t_tensor * 1e3}
         entry["bound"] = "tensor" if t_tensor > t_hbm else "hbm"
         if name in alg_flops:
-            entry["frac_tensor_exact_peak"] = entry["alg_tflops"] / exact_peak
+            entry["tensor_ceiling_tflops"] = ceiling
+            entry["frac_tensor_exact_peak"] = entry["alg_tflops"] / ceiling
     # the kernel with the largest share of the step
-    dominant = max((k for k in kernels if k in alg_bytes), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
+    dominant = max((k for k in kernels if "alg_bytes" in kernels[k] and k != "pack"),
+                   key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
     dk = kernels[dominant]
     if dk["bound"] == "tensor":
         roofline = {
-            "kernel": dk["kernel"], "bound": "tensor", "achieved": dk["alg_tflops"], "peak": exact_peak, "unit": "TFLOP/s",
-            "frac": dk["alg_tflops"] / exact_peak, "traffic": NCU_TRAFFIC.get(dominant) if args.dtype == "f32" else None,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 rate) / 3 (3xTF32 products per fp32 product)"
-                           if args.dtype == "f32" else "MEASURED_PEAKS.json bf16_tflops_sustained",
-            "note": "dominant kernel by time. achieved = the reference's fp32 multiply-adds (x2) per launch / launch time; the "
-                    "kernel issues 3 kind::tf32 MMAs per product to stay fp32-exact, so its tensor floor exceeds its HBM floor "
-                    "(kernels[*].floor_ms).  The HBM-bound kernel proper is the segmented reduce (kernels.reduce.frac_hbm).",
+            "kernel": dk["kernel"], "bound": "tensor", "achieved": dk["alg_tflops"], "peak": dk["tensor_ceiling_tflops"], "unit": "TFLOP/s",
+            "frac": dk["frac_tensor_exact_peak"], "traffic": traffic.get(dominant), "traffic_source": traffic_src,
+            "peak_source": tensor_src + " / %g (MMAs issued per fp32-exact product x rate ratio)" % exact_div.get(dominant, 1.0),
+            "note": "dominant kernel by time. achieved = the reference's multiply-adds (x2) per launch / CUDA-event launch time; "
+                    "kernels[*].floor_ms has both floors and kernels[*].frac_hbm the bandwidth view.",
         }
     else:
         roofline = {
             "kernel": dk["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": dk["frac_hbm"], "traffic": NCU_TRAFFIC.get(dominant) if args.dtype == "f32" else None, "peak_source": peak_src,
-            "note": "dominant kernel by time; algorithmic bytes per launch / launch time (kernels[*].floor_ms has both floors)",
+            "frac": dk["frac_hbm"], "traffic": traffic.get(dominant), "traffic_source": traffic_src, "peak_source": peak_src,
+            "note": "dominant kernel by time; algorithmic bytes per launch / CUDA-event launch time (kernels[*].floor_ms has both floors)",
         }
     b_min = 2 * n_nodes * HIDDEN * esz + 8 * E + (T * D * HIDDEN + 6 * HIDDEN * HIDDEN + 6 * HIDDEN) * esz
     layer_ms = ms_step / NUM_LAYERS

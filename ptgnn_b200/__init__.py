@@ -14,10 +14,12 @@ from .messagepassing import (
     GatedMessagePassingLayer,
     MlpMessagePassingLayer,
 )
+from .residuallayers import ConcatResidualLayer, LinearResidualLayer, MeanResidualLayer
 from .scatter import scatter, scatter_add, scatter_max, scatter_mean, scatter_min, scatter_sum
 
 __all__ = [
     "EdgePlan", "plan_for", "clear_plan_cache", "GnnOutput", "GraphNeuralNetwork", "MLP", "AbstractMessageAggregation",
-    "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "scatter", "scatter_add",
+    "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "MeanResidualLayer",
+    "ConcatResidualLayer", "LinearResidualLayer", "scatter", "scatter_add",
     "scatter_sum", "scatter_mean", "scatter_max", "scatter_min",
 ]

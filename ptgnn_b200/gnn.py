@@ -32,9 +32,27 @@ class GnnOutput(NamedTuple):
         return self.node_graph_idx_reference
 
 
+def register_with_reference_metrics() -> bool:
+    """Makes ``GraphNeuralNetwork`` a (virtual) subclass of the reference's ``ModuleWithMetrics`` if that class has been
+    imported: reference parents collect and reset child metrics with ``isinstance(child, ModuleWithMetrics)``
+    (`/root/reference/ptgnn/baseneuralmodel/modulewithmetrics.py:44-46,56-57`).  ``ModuleWithMetrics`` is an ``ABC``, so
+    registration is all it takes; idempotent, never imports the reference itself.  Called when a container is constructed (by
+    then any reference parent has imported the class) and by ``ptgnn_b200.overlay.install()``."""
+    import sys
+
+    mod = sys.modules.get("ptgnn.baseneuralmodel.modulewithmetrics")
+    base = getattr(mod, "ModuleWithMetrics", None)
+    if base is None or not hasattr(base, "register"):
+        return False
+    if not issubclass(GraphNeuralNetwork, base):
+        base.register(GraphNeuralNetwork)
+    return True
+
+
 class GraphNeuralNetwork(nn.Module):
-    """Generic message-passing GNN over discrete edge types (duck-types the reference's ``ModuleWithMetrics``:
-    ``report_metrics`` / ``reset_metrics`` / ``_module_metrics`` / ``_reset_module_metrics``)."""
+    """Generic message-passing GNN over discrete edge types.  Implements the reference's ``ModuleWithMetrics`` protocol
+    (``report_metrics`` / ``reset_metrics`` / ``_module_metrics`` / ``_reset_module_metrics``) and registers itself as a virtual
+    subclass of the reference's class when that is loaded, so that it also works as a CHILD of reference modules."""
 
     def __init__(
         self,
@@ -54,6 +72,7 @@ class GraphNeuralNetwork(nn.Module):
         self.__edge_dropout_rate = edge_dropout_rate
         self.__edge_feature_embedder = edge_feature_embedder
         self._reset_module_metrics()
+        register_with_reference_metrics()
 
     # ---- metrics protocol (modulewithmetrics.py:8-77) ---------------------------------------------
     def _reset_module_metrics(self) -> None:

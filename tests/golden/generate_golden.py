@@ -126,5 +126,60 @@ def main():
          **{"last::" + k: v.numpy() for k, v in last.state_dict().items()})
 
 
+def main_round2():
+    """Round-2 fixtures: (1) the reference's OWN bf16 path -- fp32 modules under torch.autocast("cpu", bfloat16), the AMP
+    arithmetic of trainer.py:221 -- next to its fp32 output on the same inputs (the gap between the two is what any bf16
+    bar has to be read against); (2) a Typilus-GGNN-style stack with the reference's ConcatResidualLayer between gated layers
+    (typilus/train.py:39-65) through the reference container."""
+    from ptgnn.neuralmodels.gnn.messagepassing.residuallayers import ConcatResidualLayer
+
+    for i, (kind, agg) in enumerate([("gated", "sum"), ("gated", "max"), ("mlp", "sum"), ("mlp", "max")]):
+        gen = torch.Generator().manual_seed(700 + i)
+        torch.manual_seed(800 + i)
+        n, H, counts = 384, 128, [900, 0, 500, 260]
+        adj = random_graph(gen, n - 16, counts)
+        h = torch.randn(n, H, generator=gen)
+        if kind == "gated":
+            layer = GatedMessagePassingLayer(H, H, len(counts), agg)
+        else:
+            layer = MlpMessagePassingLayer(H, H, H, len(counts), agg)
+        out32 = run_layer(layer, h, adj)
+        hb = h.to(torch.bfloat16)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out_ac = run_layer(layer, hb, adj)
+        out32_on_rounded = run_layer(layer, hb.float(), adj)
+        gap = (out_ac.float() - out32_on_rounded).abs()
+        print(f"{kind}_{agg}_bf16ac: autocast output dtype {out_ac.dtype}; autocast vs fp32 (same rounded inputs): max {gap.max():.3e} "
+              f"mean {gap.mean():.3e} within 1e-2: {(gap <= 1e-2 * out32_on_rounded.abs().clamp(min=1)).float().mean():.4f}")
+        save(f"{kind}_{agg}_bf16ac", h=h.numpy(), out_autocast=out_ac.float().numpy(), out_fp32=out32.numpy(),
+             out_fp32_rounded_inputs=out32_on_rounded.numpy(), agg=agg, **pack("", adj), **state(layer))
+
+    gen = torch.Generator().manual_seed(900)
+    torch.manual_seed(901)
+    n, H = 300, 64
+    raw = random_graph(gen, n, [500, 0, 140])
+    T = 2 * len(raw) + 1
+    shared = GatedMessagePassingLayer(H, H, T, "max")
+    last = GatedMessagePassingLayer(2 * H, H, T, "max")
+    r1 = ConcatResidualLayer(H)
+
+    class Embed(torch.nn.Module):
+        def forward(self, x):
+            return x
+
+    gnn = GraphNeuralNetwork([r1.pass_through_dummy_layer(), shared, shared, shared, r1, last], Embed(),
+                             introduce_backwards_edges=True, add_self_edges=True)
+    gnn.eval()
+    h = torch.randn(n, H, generator=gen)
+    with torch.no_grad():
+        res = gnn(node_data={"x": h}, adjacency_lists=list(raw), edge_feature_data=[], node_to_graph_idx=torch.zeros(n, dtype=torch.int64),
+                  reference_node_ids={}, reference_node_graph_idx={}, num_graphs=2)
+    save("gnn_residual", h=h.numpy(), out=res.output_node_representations.numpy(), **pack("", raw),
+         **{"shared::" + k: v.numpy() for k, v in shared.state_dict().items()},
+         **{"last::" + k: v.numpy() for k, v in last.state_dict().items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--round2-only" not in sys.argv:
+        main()
+    main_round2()
