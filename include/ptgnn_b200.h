@@ -87,6 +87,17 @@ int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes /* bound f
                           int32_t *pos, int32_t *src_sorted, uint8_t *etype_sorted, int32_t *src32, int32_t *tgt32,
                           int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The two phases of ptgnn_b200_plan_build as separate calls.  `plan_convert` = down-conversion, range check, in-degree
+ * histogram, row_ptr (everything the fused layer kernels and the block plan need); `plan_sort` = the stable sort by target and
+ * the sorted arrays (needed by the unfused layer kernels and by ptgnn_b200_segment_reduce_f32 callers).  Same workspace size. */
+int ptgnn_b200_plan_convert(int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
+                            const int64_t *const *src_ptrs /*[host]*/, const int64_t *const *tgt_ptrs /*[host]*/,
+                            const int64_t *counts /*[host]*/, int32_t *row_ptr, int32_t *src32, int32_t *tgt32, int32_t *status,
+                            void *workspace, size_t workspace_bytes, void *stream);
+int ptgnn_b200_plan_sort(int64_t num_nodes, int32_t num_types, const int64_t *counts /*[host]*/, int32_t *perm, int32_t *pos,
+                         int32_t *src_sorted, uint8_t *etype_sorted, const int32_t *src32, const int32_t *tgt32,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Segmented reduce -- replaces torch_scatter.scatter(src, index, dim=0, dim_size=N, reduce) as called
  * at abstractmessagepassing.py:44-50.  `messages` is [E, D] fp32.  If `perm` is NULL the rows are

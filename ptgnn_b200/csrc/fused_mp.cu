@@ -6,6 +6,8 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace ptgnn {
@@ -127,6 +129,30 @@ struct StepGen {
     }
 };
 
+// One accumulator column of the epilogue: acc = op(start ? pre : acc, v), then agg_s[addr] = acc if the column ends its segment.
+// Two predicated ops instead of select + op keep the serial chain at one ALU latency per column; shared-space 32-bit addresses.
+template <int RED>
+__device__ __forceinline__ void chain_step(float &acc, float pre, float v, uint32_t start_bit, uint32_t end_bit, uint32_t addr) {
+    if (RED == PTGNN_REDUCE_MAX) {
+        asm volatile("{\n\t.reg .pred ps, pe;\n\tsetp.ne.u32 ps, %3, 0;\n\tsetp.ne.u32 pe, %4, 0;\n\t"
+                     "@ps max.f32 %0, %1, %2;\n\t@!ps max.f32 %0, %0, %2;\n\t@pe st.shared.f32 [%5], %0;\n\t}"
+                     : "+f"(acc) : "f"(pre), "f"(v), "r"(start_bit), "r"(end_bit), "r"(addr) : "memory");
+    } else if (RED == PTGNN_REDUCE_MIN) {
+        asm volatile("{\n\t.reg .pred ps, pe;\n\tsetp.ne.u32 ps, %3, 0;\n\tsetp.ne.u32 pe, %4, 0;\n\t"
+                     "@ps min.f32 %0, %1, %2;\n\t@!ps min.f32 %0, %0, %2;\n\t@pe st.shared.f32 [%5], %0;\n\t}"
+                     : "+f"(acc) : "f"(pre), "f"(v), "r"(start_bit), "r"(end_bit), "r"(addr) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred ps, pe;\n\tsetp.ne.u32 ps, %3, 0;\n\tsetp.ne.u32 pe, %4, 0;\n\t"
+                     "@ps add.f32 %0, %1, %2;\n\t@!ps add.f32 %0, %0, %2;\n\t@pe st.shared.f32 [%5], %0;\n\t}"
+                     : "+f"(acc) : "f"(pre), "f"(v), "r"(start_bit), "r"(end_bit), "r"(addr) : "memory");
+    }
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 template <int RED> __device__ __forceinline__ float red_identity() {
     return RED == PTGNN_REDUCE_MAX ? -FLT_MAX : (RED == PTGNN_REDUCE_MIN ? FLT_MAX : 0.0f);
 }
@@ -154,7 +180,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
     constexpr uint32_t FMT = NPROD == 3 ? 0u /*F16*/ : tc::FMT_BF16;
 
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte aligned ring; the pad is added as an OFFSET so that the pointers keep the shared address space (an integer
+    // round trip makes every access a generic LD/ST with 64-bit address arithmetic)
+    unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float *agg_s = reinterpret_cast<float *>(ring + AGG_OFF);
     unsigned char *tail = ring + AGG_OFF + agg_bytes(p.B);
     Meta *meta_ring = reinterpret_cast<Meta *>(tail);
@@ -300,47 +328,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             const int q = g & 7, rsub = g >> 3;
             StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
             uint32_t c_issue = 0, c_done = 0, sgc = 0;
-            bool more = true;
-            auto issue_next = [&]() {
-                Step s;
+            // Everything a step needs from global memory (row indices, the targets of its columns) is loaded ONE STEP AHEAD:
+            // `fetch` only issues the loads, the copies of the current step are issued while they are in flight, `finish_meta`
+            // consumes them afterwards.
+            Step cur, nxt;
+            bool has_nxt = false;
+            int idx_nxt[NMAX / 8];
+            int tl_a[NMAX / 64], tl_b[NMAX / 64];
+            auto fetch = [&]() {                       // -> nxt, idx_nxt, tl_a / tl_b (raw loads only)
                 int ev;
-                do { ev = gen.next(s); } while (ev == 1);
-                if (ev == 2) { more = false; return; }
-                int idx[NMAX / 8];
-                if (s.seg == 0) {
+                do { ev = gen.next(nxt); } while (ev == 1);
+                has_nxt = ev == 0;
+                if (!has_nxt) return;
+                if (nxt.seg == 0) {
 #pragma unroll
                     for (int i = 0; i < NMAX / 8; ++i) {
                         const int r = rsub + 8 * i;
-                        idx[i] = r < s.n ? __ldg(p.src_f + s.e + r) : -1;
+                        idx_nxt[i] = r < nxt.n ? __ldg(p.src_f + nxt.e + r) : -1;
+                    }
+#pragma unroll
+                    for (int half = 0; half < NMAX / 64; ++half) {
+                        const int c = g + 64 * half;
+                        tl_a[half] = c < nxt.n ? (int)__ldg(p.tl_f + nxt.e + c) : -1;
+                        tl_b[half] = c + 1 < nxt.n ? (int)__ldg(p.tl_f + nxt.e + c + 1) : -2;
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < NMAX / 8; ++i) {
                         const int r = rsub + 8 * i;
-                        idx[i] = r < s.n ? s.blk * p.B + (int)__ldg(p.tl_f + s.e + r) : -1;
+                        idx_nxt[i] = r < nxt.n ? nxt.blk * p.B + (int)__ldg(p.tl_f + nxt.e + r) : -1;
                     }
                 }
-                if (s.seg == 0) {       // column metadata for the epilogue (columns g and g + 64)
-                    Meta *m = &meta_ring[sgc % META_RING];
+            };
+            auto finish_meta = [&]() {                 // column metadata of `nxt` for the epilogue (columns g and g + 64)
+                if (!has_nxt || nxt.seg != 0) return;
+                Meta *m = &meta_ring[sgc % META_RING];
 #pragma unroll
-                    for (int half = 0; half < NMAX / 64; ++half) {
-                        const int c = g + 64 * half;
-                        int tl = 0;
-                        bool end = false;
-                        if (c < s.n) {
-                            tl = (int)__ldg(p.tl_f + s.e + c);
-                            end = c == s.n - 1 || (int)__ldg(p.tl_f + s.e + c + 1) != tl;
-                        }
-                        m->tloff[c] = tl * (kD * 4);
-                        const uint32_t word = __ballot_sync(0xffffffffu, end);
-                        if (lane == 0) m->endmask[c >> 5] = word;
-                    }
-                    if (g == 0) m->n = s.n;
-                    ++sgc;
+                for (int half = 0; half < NMAX / 64; ++half) {
+                    const int c = g + 64 * half;
+                    const bool valid = tl_a[half] >= 0;
+                    const bool end = valid && tl_b[half] != tl_a[half];      // last column (tl_b = -2) or the target changes
+                    m->tloff[c] = valid ? tl_a[half] * (kD * 4) : 0;
+                    const uint32_t word = __ballot_sync(0xffffffffu, end);
+                    if (lane == 0) m->endmask[c >> 5] = word;
                 }
+                if (g == 0) m->n = nxt.n;
+                ++sgc;
+            };
+            auto issue_next = [&]() {                  // issue the copies of `nxt`, prefetch the step after it
+                cur = nxt;
+                int idx[NMAX / 8];
+#pragma unroll
+                for (int i = 0; i < NMAX / 8; ++i) idx[i] = idx_nxt[i];
+                fetch();
                 const uint32_t slot = c_issue % NUM_SLOTS;
                 mbar_wait(&x_empty[slot], ((c_issue / NUM_SLOTS) & 1) ^ 1);
-                const unsigned char *rows = s.seg == 0 ? p.src_rows : p.tgt_rows;
+                const unsigned char *rows = cur.seg == 0 ? p.src_rows : p.tgt_rows;
                 const uint32_t sbase = smem_u32(ring + slot * SLOT_BYTES) + swz(rsub, q);
 #pragma unroll
                 for (int i = 0; i < NMAX / 8; ++i) {
@@ -352,10 +395,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     }
                 }
                 ++c_issue;
+                finish_meta();
             };
+            fetch();
+            finish_meta();
+            bool more = has_nxt;
 #pragma unroll
             for (int i = 0; i < LOOKAHEAD; ++i) {
-                if (more) issue_next();
+                if (more) { issue_next(); more = has_nxt; }
                 cp_async_commit();
             }
             while (c_done < c_issue) {
@@ -363,7 +410,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 tc::fence_proxy_async_smem();            // ... and are visible to the tensor core (async proxy)
                 mbar_arrive(&x_full[c_done % NUM_SLOTS]);
                 ++c_done;
-                if (more) issue_next();
+                if (more) { issue_next(); more = has_nxt; }
                 cp_async_commit();
             }
             cp_async_wait<0>();
@@ -378,7 +425,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
         const int ew = warp - EPI_WARP0;
         const int d = ew * 32 + lane;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC_TMEM_OFF;
-        unsigned char *aggcol = reinterpret_cast<unsigned char *>(agg_s + d);
+        const uint32_t aggcol_s = smem_u32(agg_s + d);      // shared-space address of agg_s[0][d]
         const float IDENT = red_identity<RED>();
         StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
         for (int r = 0; r < p.B; ++r) agg_s[r * kD + d] = IDENT;
@@ -396,32 +443,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 const Meta *m = &meta_ring[sg % META_RING];
                 const int n = s.n;
                 uint32_t carry = 1u;                       // the first column of a sub-group always (re)loads its target's value
-                for (int c0 = 0; c0 < n; c0 += 32) {
-                    uint32_t vm[32], vc[32];
-                    tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
-                    if (NPROD == 3) tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
-                    int off[32];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int4 o = *reinterpret_cast<const int4 *>(&m->tloff[c0 + 4 * j]);
-                        off[4 * j] = o.x; off[4 * j + 1] = o.y; off[4 * j + 2] = o.z; off[4 * j + 3] = o.w;
+                // W = 32 or 16 accumulator columns per batch (tails of <= 16 columns take the narrow form)
+                auto batch = [&](auto width_tag, int c0) {
+                    constexpr int W = decltype(width_tag)::value;
+                    uint32_t vm[W], vc[W];
+                    if (W == 32) {
+                        tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + c0, reinterpret_cast<uint32_t (&)[32]>(vm));
+                        if (NPROD == 3) tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, reinterpret_cast<uint32_t (&)[32]>(vc));
+                    } else {
+                        tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, reinterpret_cast<uint32_t (&)[16]>(vm));
+                        if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, reinterpret_cast<uint32_t (&)[16]>(vc));
                     }
-                    const uint32_t endw = m->endmask[c0 >> 5];
-                    const uint32_t startw = (endw << 1) | carry;
-                    carry = endw >> 31;
-                    float pre[32];
+                    uint32_t addr[W];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) pre[c] = *reinterpret_cast<const float *>(aggcol + off[c]);
+                    for (int j = 0; j < W / 4; ++j) {
+                        const int4 o = *reinterpret_cast<const int4 *>(&m->tloff[c0 + 4 * j]);
+                        addr[4 * j] = aggcol_s + o.x; addr[4 * j + 1] = aggcol_s + o.y;
+                        addr[4 * j + 2] = aggcol_s + o.z; addr[4 * j + 3] = aggcol_s + o.w;
+                    }
+                    uint32_t endw = m->endmask[c0 >> 5] >> (c0 & 31);
+                    if (W == 16) endw &= 0xFFFFu;
+                    const uint32_t startw = (endw << 1) | carry;
+                    carry = (endw >> (W - 1)) & 1u;
+                    float pre[W];
+#pragma unroll
+                    for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
+                    for (int c = 0; c < W; ++c) {
                         float v = __uint_as_float(vm[c]);
                         if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
                         else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
-                        if ((startw >> c) & 1u) acc = pre[c];
-                        acc = red_op<RED>(acc, v);
-                        if ((endw >> c) & 1u) *reinterpret_cast<float *>(aggcol + off[c]) = acc;
+                        chain_step<RED>(acc, pre[c], v, startw & (1u << c), endw & (1u << c), addr[c]);
                     }
+                };
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    if (n - c0 <= 16) batch(std::integral_constant<int, 16>{}, c0);
+                    else batch(std::integral_constant<int, 32>{}, c0);
                 }
                 tc::tc_fence_before_sync();
                 __syncwarp();

@@ -307,7 +307,8 @@ static int sort_edges_by_target(const int32_t *tgt32, int64_t N, int64_t E, int3
 
 // =================================================================================================
 // block plan for the fused gather -> Linear -> reduce kernel (fused_mp.cu): edges sorted, stably, by
-// (target block, edge type, target).  key = block << 16 | type << 8 | (target - block * B);  B <= 256, types <= 128.
+// (target block, edge type, target).  key = (block * T + type) * B + (target - block * B) < ceil(N / B) * T * B: for config 2
+// that is 22 bits = three 8-bit radix passes.  B <= 256, types <= 128.
 // =================================================================================================
 __global__ void __launch_bounds__(256) block_keys_kernel(const __grid_constant__ TypeOffsets toff, int64_t num_edges,
                                                          const int32_t *__restrict__ tgt32, int B, int32_t *__restrict__ keys,
@@ -316,17 +317,17 @@ __global__ void __launch_bounds__(256) block_keys_kernel(const __grid_constant__
         const int t = type_of_edge(toff.off, toff.num_types, e);
         const int v = tgt32[e];
         const int blk = v / B, tl = v - blk * B;
-        keys[e] = (blk << 16) | (t << 8) | tl;
+        keys[e] = (blk * toff.num_types + t) * B + tl;
         atomicAdd(&group_count[(int64_t)blk * toff.num_types + t], 1);
     }
 }
-__global__ void __launch_bounds__(256) block_finalize_kernel(int64_t num_edges, const int32_t *__restrict__ perm,
+__global__ void __launch_bounds__(256) block_finalize_kernel(int64_t num_edges, int B, const int32_t *__restrict__ perm,
                                                              const int32_t *__restrict__ sorted_keys,
                                                              const int32_t *__restrict__ src32, int32_t *__restrict__ src_f,
                                                              uint8_t *__restrict__ tl_f) {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < num_edges; j += (int64_t)gridDim.x * blockDim.x) {
         src_f[j] = src32[perm[j]];
-        tl_f[j] = (uint8_t)(sorted_keys[j] & 0xFF);
+        tl_f[j] = (uint8_t)(sorted_keys[j] % B);
     }
 }
 struct BlockPlanWs { size_t keys, perm, scan_sums, plan, total; };
@@ -352,12 +353,11 @@ extern "C" size_t ptgnn_b200_plan_workspace_bytes(int64_t num_nodes, int64_t num
     return plan_ws_layout(num_nodes, num_edges).total;
 }
 
-extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
-                                     const int64_t *const *src_ptrs,
-                                     const int64_t *const *tgt_ptrs, const int64_t *counts, int32_t *row_ptr,
-                                     int32_t *perm, int32_t *pos, int32_t *src_sorted, uint8_t *etype_sorted,
-                                     int32_t *src32, int32_t *tgt32, int32_t *status, void *workspace,
-                                     size_t workspace_bytes, void *stream) {
+// phases: 1 = down-convert + in-degree histogram + row_ptr, 2 = stable sort by target + sorted arrays, 3 = both
+static int plan_build_phases(int phases, int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
+                             const int64_t *const *src_ptrs, const int64_t *const *tgt_ptrs, const int64_t *counts, int32_t *row_ptr,
+                             int32_t *perm, int32_t *pos, int32_t *src_sorted, uint8_t *etype_sorted, int32_t *src32, int32_t *tgt32,
+                             int32_t *status, void *workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PTGNN_CHECK_ARG(num_nodes >= 0 && num_nodes < INT32_MAX, "plan_build: num_nodes=%lld out of range", (long long)num_nodes);
     if (num_source_nodes <= 0) num_source_nodes = num_nodes;
@@ -371,9 +371,9 @@ extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes
     int64_t E = 0;
     for (int t = 0; t < num_types; ++t) {
         PTGNN_CHECK_ARG(counts[t] >= 0, "plan_build: negative edge count for type %d", t);
-        PTGNN_CHECK_ARG(counts[t] == 0 || (src_ptrs[t] && tgt_ptrs[t]), "plan_build: null edge list for type %d", t);
-        tabs.src[t] = src_ptrs[t];
-        tabs.tgt[t] = tgt_ptrs[t];
+        PTGNN_CHECK_ARG(counts[t] == 0 || !(phases & 1) || (src_ptrs[t] && tgt_ptrs[t]), "plan_build: null edge list for type %d", t);
+        tabs.src[t] = (phases & 1) ? src_ptrs[t] : nullptr;
+        tabs.tgt[t] = (phases & 1) ? tgt_ptrs[t] : nullptr;
         tabs.off[t] = E;
         toff.off[t] = (int32_t)E;
         E += counts[t];
@@ -391,24 +391,28 @@ extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes
     char *ws = static_cast<char *>(workspace);
     int32_t *deg = reinterpret_cast<int32_t *>(ws + L.deg);
 
-    PTGNN_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
-    PTGNN_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (size_t)(num_nodes + 1), st));
-    if (E == 0) {
-        PTGNN_CUDA(cudaMemsetAsync(row_ptr, 0, sizeof(int32_t) * (size_t)(num_nodes + 1), st));
-        return PTGNN_OK;
+    const unsigned grid = (unsigned)(ceil_div(E > 0 ? E : 1, 256) < 148 * 16 ? ceil_div(E > 0 ? E : 1, 256) : 148 * 16);
+    int rc = PTGNN_OK;
+    if (phases & 1) {
+        PTGNN_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+        PTGNN_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (size_t)(num_nodes + 1), st));
+        if (E == 0) {
+            PTGNN_CUDA(cudaMemsetAsync(row_ptr, 0, sizeof(int32_t) * (size_t)(num_nodes + 1), st));
+            return PTGNN_OK;
+        }
+        PTGNN_CHECK_ARG(src32 && tgt32, "plan_build: null output array");
+        PTGNN_CHECK_ARG(num_nodes > 0, "plan_build: edges given but num_nodes == 0");
+        {
+            TimedScope timed__(PTGNN_KERNEL_PLAN, st);
+            convert_count_kernel<<<grid, 256, 0, st>>>(tabs, num_nodes, num_source_nodes, E, src32, tgt32, deg, status);
+        }
+        PTGNN_LAUNCHED();
+        // row_ptr[0..N] = exclusive scan of deg[0..N] (deg[N] == 0, so row_ptr[N] == E)
+        rc = exclusive_scan_i32(deg, row_ptr, num_nodes + 1, reinterpret_cast<int32_t *>(ws + L.scan_sums), nullptr, st);
+        if (rc) return rc;
     }
+    if (!(phases & 2) || E == 0) return PTGNN_OK;
     PTGNN_CHECK_ARG(perm && pos && src_sorted && etype_sorted && src32 && tgt32, "plan_build: null output array");
-    PTGNN_CHECK_ARG(num_nodes > 0, "plan_build: edges given but num_nodes == 0");
-
-    const unsigned grid = (unsigned)(ceil_div(E, 256) < 148 * 16 ? ceil_div(E, 256) : 148 * 16);
-    {
-        TimedScope timed__(PTGNN_KERNEL_PLAN, st);
-        convert_count_kernel<<<grid, 256, 0, st>>>(tabs, num_nodes, num_source_nodes, E, src32, tgt32, deg, status);
-    }
-    PTGNN_LAUNCHED();
-    // row_ptr[0..N] = exclusive scan of deg[0..N] (deg[N] == 0, so row_ptr[N] == E)
-    int rc = exclusive_scan_i32(deg, row_ptr, num_nodes + 1, reinterpret_cast<int32_t *>(ws + L.scan_sums), nullptr, st);
-    if (rc) return rc;
     rc = sort_edges_by_target(tgt32, num_nodes, E, perm, ws, L, st);
     if (rc) return rc;
     {
@@ -417,6 +421,30 @@ extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
+}
+
+extern "C" int ptgnn_b200_plan_build(int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
+                                     const int64_t *const *src_ptrs, const int64_t *const *tgt_ptrs, const int64_t *counts,
+                                     int32_t *row_ptr, int32_t *perm, int32_t *pos, int32_t *src_sorted, uint8_t *etype_sorted,
+                                     int32_t *src32, int32_t *tgt32, int32_t *status, void *workspace, size_t workspace_bytes,
+                                     void *stream) {
+    return plan_build_phases(3, num_nodes, num_source_nodes, num_types, src_ptrs, tgt_ptrs, counts, row_ptr, perm, pos, src_sorted,
+                             etype_sorted, src32, tgt32, status, workspace, workspace_bytes, stream);
+}
+extern "C" int ptgnn_b200_plan_convert(int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,
+                                       const int64_t *const *src_ptrs, const int64_t *const *tgt_ptrs, const int64_t *counts,
+                                       int32_t *row_ptr, int32_t *src32, int32_t *tgt32, int32_t *status, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+    return plan_build_phases(1, num_nodes, num_source_nodes, num_types, src_ptrs, tgt_ptrs, counts, row_ptr, nullptr, nullptr, nullptr,
+                             nullptr, src32, tgt32, status, workspace, workspace_bytes, stream);
+}
+extern "C" int ptgnn_b200_plan_sort(int64_t num_nodes, int32_t num_types, const int64_t *counts, int32_t *perm, int32_t *pos,
+                                    int32_t *src_sorted, uint8_t *etype_sorted, const int32_t *src32, const int32_t *tgt32,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    int32_t dummy_status = 0;
+    return plan_build_phases(2, num_nodes, num_nodes, num_types, nullptr, nullptr, counts, &dummy_status /* non-null, unused */, perm, pos,
+                             src_sorted, etype_sorted, const_cast<int32_t *>(src32), const_cast<int32_t *>(tgt32), &dummy_status, workspace,
+                             workspace_bytes, stream);
 }
 
 extern "C" size_t ptgnn_b200_block_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_types,
@@ -437,7 +465,8 @@ extern "C" int ptgnn_b200_block_plan_build(int64_t num_nodes, int32_t num_types,
     const int64_t E = type_off[T];
     PTGNN_CHECK_ARG(E >= 0 && E < INT32_MAX, "block_plan_build: edge count out of range");
     const int64_t nblk = ceil_div(num_nodes, B), groups = nblk * T;
-    PTGNN_CHECK_ARG(nblk < (1 << 15), "block_plan_build: %lld target blocks do not fit the 15-bit key field", (long long)nblk);
+    PTGNN_CHECK_ARG(nblk * T * B < ((int64_t)1 << 31), "block_plan_build: %lld blocks x %d types x %d targets overflow the 31-bit sort key",
+                    (long long)nblk, T, B);
     PTGNN_CHECK_ARG(group_off, "block_plan_build: null group_off");
     const BlockPlanWs L = block_plan_ws_layout(num_nodes, E, T, B);
     if (workspace_bytes < L.total || !workspace) {
@@ -461,11 +490,11 @@ extern "C" int ptgnn_b200_block_plan_build(int64_t num_nodes, int32_t num_types,
     int rc = exclusive_scan_i32(group_off, group_off, groups + 1, reinterpret_cast<int32_t *>(ws + L.scan_sums), nullptr, st);
     if (rc) return rc;
     const int32_t *sorted_keys = nullptr;
-    rc = sort_edges_by_key(keys, 16 + bits_for(nblk), E, perm, ws + L.plan, plan_ws_layout(num_nodes, E), st, &sorted_keys);
+    rc = sort_edges_by_key(keys, bits_for(nblk * T * B), E, perm, ws + L.plan, plan_ws_layout(num_nodes, E), st, &sorted_keys);
     if (rc) return rc;
     {
         TimedScope timed__(PTGNN_KERNEL_PLAN, st);
-        block_finalize_kernel<<<grid, 256, 0, st>>>(E, perm, sorted_keys, src32, src_f, tl_f);
+        block_finalize_kernel<<<grid, 256, 0, st>>>(E, B, perm, sorted_keys, src32, src_f, tl_f);
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;

@@ -51,7 +51,7 @@ struct Segment {        // one K-range of the tile's GEMM (all element counts in
 template <class Policy>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_pipeline_bf16_kernel(const __grid_constant__ typename Policy::Params p) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset form: keeps the shared address space
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + RING_BYTES);
     uint64_t *full = bars, *empty = bars + NUM_SLOTS, *landed = bars + 2 * NUM_SLOTS;
     uint64_t *tmem_full = bars + 3 * NUM_SLOTS, *tmem_empty = bars + 3 * NUM_SLOTS + 2;

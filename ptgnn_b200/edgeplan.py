@@ -22,8 +22,7 @@ class EdgePlan:
     """Device-resident CSR-by-target plan (all int32 unless noted).  Field meanings: include/ptgnn_b200.h."""
 
     __slots__ = (
-        "num_nodes", "num_source_nodes", "num_edges", "num_types", "type_off", "type_off_c", "row_ptr", "perm", "pos", "src_sorted",
-        "etype_sorted", "src32", "tgt32", "status", "device", "_keepalive", "_validated", "_block",
+        "num_nodes", "num_source_nodes", "num_edges", "num_types", "type_off", "type_off_c", "row_ptr", "src32", "tgt32", "status", "device", "_keepalive", "_validated", "_block", "_sorted", "_counts_c",
     )
 
     # status words (pinned host memory the kernels write directly, so the host can poll them without synchronising):
@@ -57,25 +56,51 @@ class EdgePlan:
         def i32(n):
             return torch.empty(n, dtype=torch.int32, device=device)
 
+        # phase 1 now (int32 edge lists, range check, row_ptr); the target-sorted arrays are built on first use (`_sorted`):
+        # layers that run on the fused kernel only need phase 1 + the block plan
         self.row_ptr = i32(num_nodes + 1)
-        self.perm, self.pos, self.src_sorted, self.src32, self.tgt32 = i32(E), i32(E), i32(E), i32(E), i32(E)
-        self.etype_sorted = torch.empty(E, dtype=torch.uint8, device=device)
+        self.src32, self.tgt32 = i32(E), i32(E)
+        self._sorted = None
         self.status = torch.zeros(self.STATUS_WORDS, dtype=torch.int32).pin_memory()
         self._block = None
+        self._counts_c = N.i64_array(counts)
         lib = N.lib()
         ws_bytes = lib.ptgnn_b200_plan_workspace_bytes(num_nodes, E)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):
-            rc = lib.ptgnn_b200_plan_build(
-                num_nodes, self.num_source_nodes, len(counts), N.ptr_table(srcs), N.ptr_table(tgts), N.i64_array(counts),
-                N.ptr(self.row_ptr), N.ptr(self.perm), N.ptr(self.pos), N.ptr(self.src_sorted), N.ptr(self.etype_sorted),
-                N.ptr(self.src32), N.ptr(self.tgt32), N.ptr(self.status), N.ptr(ws), ws_bytes, N.current_stream(device),
+            rc = lib.ptgnn_b200_plan_convert(
+                num_nodes, self.num_source_nodes, len(counts), N.ptr_table(srcs), N.ptr_table(tgts), self._counts_c,
+                N.ptr(self.row_ptr), N.ptr(self.src32), N.ptr(self.tgt32), N.ptr(self.status), N.ptr(ws), ws_bytes,
+                N.current_stream(device),
             )
-        N.check(rc, "ptgnn_b200_plan_build")
+        N.check(rc, "ptgnn_b200_plan_convert")
         self._keepalive = (srcs, tgts)
         self._validated = False
         if validate:
             self.validate()
+
+    # ---- target-sorted arrays (unfused kernels, scatter): built on first access ---------------------------------------------
+    def _sort(self):
+        if self._sorted is None:
+            E, dev = self.num_edges, self.device
+            perm, pos, src_sorted = (torch.empty(E, dtype=torch.int32, device=dev) for _ in range(3))
+            etype_sorted = torch.empty(E, dtype=torch.uint8, device=dev)
+            if E:
+                lib = N.lib()
+                ws_bytes = lib.ptgnn_b200_plan_workspace_bytes(self.num_nodes, E)
+                ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    rc = lib.ptgnn_b200_plan_sort(self.num_nodes, self.num_types, self._counts_c, N.ptr(perm), N.ptr(pos), N.ptr(src_sorted),
+                                                  N.ptr(etype_sorted), N.ptr(self.src32), N.ptr(self.tgt32), N.ptr(ws), ws_bytes,
+                                                  N.current_stream(dev))
+                N.check(rc, "ptgnn_b200_plan_sort")
+            self._sorted = (perm, pos, src_sorted, etype_sorted)
+        return self._sorted
+
+    perm = property(lambda self: self._sort()[0])
+    pos = property(lambda self: self._sort()[1])
+    src_sorted = property(lambda self: self._sort()[2])
+    etype_sorted = property(lambda self: self._sort()[3])
 
     def validate(self) -> None:
         """Synchronises the current stream and raises if the plan or a layer that used it reported an error."""

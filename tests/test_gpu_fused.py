@@ -50,7 +50,7 @@ def test_block_plan_bit_exact(n, counts):
 @pytest.mark.parametrize("n,H,counts", [
     (3001, 128, [9000, 9000, 5000, 1, 130, 0, 2000]),
     (1000, 64, [3000, 1500, 0, 700]),
-    (300, 128, [40000]),                 # ~130 edges per (block, type) target: groups split into several sub-groups
+    (300, 128, [40000]),                 # in-degree 133 for every target: groups split into several sub-groups
     (5, 128, [3, 0]),
 ])
 def test_fused_gated_vs_oracle(agg, n, H, counts):
@@ -66,7 +66,10 @@ def test_fused_gated_vs_oracle(agg, n, H, counts):
                                 **gated_oracle_args({k: v.clone().cpu() for k, v in layer.state_dict().items()}))
     with torch.no_grad():
         got = layer(h.cuda(), _dev(adj))
-    assert_close(got, ref, what=f"fused gated {agg} N={n} H={H}")
+    # 133-term sums with |agg| ~ 11: the fp32 rounding of the reference's own sequential sum is ~1e-5 there (sqrt(133) adds x
+    # half an ulp of 11), so two correct fp32 implementations differ by more than 1e-5 on this one case -> 3e-5
+    tol = 3e-5 if (counts == [40000] and agg in ("sum", "mean")) else 1e-5
+    assert_close(got, ref, tol=tol, what=f"fused gated {agg} N={n} H={H}")
 
 
 def test_fused_gated_hub_and_isolated_targets():
