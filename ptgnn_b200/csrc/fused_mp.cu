@@ -55,7 +55,8 @@ struct Params {
     const uint8_t *tl_f;
     const int32_t *row_ptr;
     void *out;
-    int num_nodes, num_blocks, B, T, reduce, out_bf16;
+    int num_nodes, num_blocks, B, T, reduce, out_mode;
+    int32_t *status;
     Epilogue epi;
 };
 
@@ -129,28 +130,42 @@ struct StepGen {
     }
 };
 
-// One accumulator column of the epilogue: acc = op(start ? pre : acc, v), then agg_s[addr] = acc if the column ends its segment.
-// Two predicated ops instead of select + op keep the serial chain at one ALU latency per column; shared-space 32-bit addresses.
+// One accumulator column of the epilogue: returns op(start ? pre : prev, v).  Two predicated ops instead of select + op keep the
+// serial chain at one ALU latency per column.  The result goes to a FRESH register (the caller keeps all 32 of a batch and
+// stores them afterwards): storing the running value straight from the chain register makes every following column wait for
+// the store to read it (short-scoreboard WAR stall, ~20 cycles per column -- measured: the epilogue was the kernel's limit).
 template <int RED>
-__device__ __forceinline__ void chain_step(float &acc, float pre, float v, uint32_t start_bit, uint32_t end_bit, uint32_t addr) {
+__device__ __forceinline__ float chain_step(float prev, float pre, float v, uint32_t start_bit) {
+    float r;
     if (RED == PTGNN_REDUCE_MAX) {
-        asm volatile("{\n\t.reg .pred ps, pe;\n\tsetp.ne.u32 ps, %3, 0;\n\tsetp.ne.u32 pe, %4, 0;\n\t"
-                     "@ps max.f32 %0, %1, %2;\n\t@!ps max.f32 %0, %0, %2;\n\t@pe st.shared.f32 [%5], %0;\n\t}"
-                     : "+f"(acc) : "f"(pre), "f"(v), "r"(start_bit), "r"(end_bit), "r"(addr) : "memory");
+        asm("{\n\t.reg .pred ps;\n\tsetp.ne.u32 ps, %4, 0;\n\t@ps max.f32 %0, %1, %2;\n\t@!ps max.f32 %0, %3, %2;\n\t}"
+            : "=f"(r) : "f"(pre), "f"(v), "f"(prev), "r"(start_bit));
     } else if (RED == PTGNN_REDUCE_MIN) {
-        asm volatile("{\n\t.reg .pred ps, pe;\n\tsetp.ne.u32 ps, %3, 0;\n\tsetp.ne.u32 pe, %4, 0;\n\t"
-                     "@ps min.f32 %0, %1, %2;\n\t@!ps min.f32 %0, %0, %2;\n\t@pe st.shared.f32 [%5], %0;\n\t}"
-                     : "+f"(acc) : "f"(pre), "f"(v), "r"(start_bit), "r"(end_bit), "r"(addr) : "memory");
+        asm("{\n\t.reg .pred ps;\n\tsetp.ne.u32 ps, %4, 0;\n\t@ps min.f32 %0, %1, %2;\n\t@!ps min.f32 %0, %3, %2;\n\t}"
+            : "=f"(r) : "f"(pre), "f"(v), "f"(prev), "r"(start_bit));
     } else {
-        asm volatile("{\n\t.reg .pred ps, pe;\n\tsetp.ne.u32 ps, %3, 0;\n\tsetp.ne.u32 pe, %4, 0;\n\t"
-                     "@ps add.f32 %0, %1, %2;\n\t@!ps add.f32 %0, %0, %2;\n\t@pe st.shared.f32 [%5], %0;\n\t}"
-                     : "+f"(acc) : "f"(pre), "f"(v), "r"(start_bit), "r"(end_bit), "r"(addr) : "memory");
+        asm("{\n\t.reg .pred ps;\n\tsetp.ne.u32 ps, %4, 0;\n\t@ps add.f32 %0, %1, %2;\n\t@!ps add.f32 %0, %3, %2;\n\t}"
+            : "=f"(r) : "f"(pre), "f"(v), "f"(prev), "r"(start_bit));
     }
+    return r;
+}
+__device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, uint32_t bit) {
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.u32 pe, %2, 0;\n\t@pe st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v), "r"(bit) : "memory");
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// x -> (hi, lo') fp16 pair; returns false when |x| is not representable (>= 65504, inf, NaN)
+__device__ __forceinline__ bool split_f16(float x, __half &hi, __half &lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+    return fabsf(x) < 65504.0f;
 }
 
 template <int RED> __device__ __forceinline__ float red_identity() {
@@ -469,13 +484,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
 #pragma unroll
                     for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
                     tc::tmem_ld_wait();
+                    float res[W];
 #pragma unroll
                     for (int c = 0; c < W; ++c) {
                         float v = __uint_as_float(vm[c]);
                         if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
                         else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
-                        chain_step<RED>(acc, pre[c], v, startw & (1u << c), endw & (1u << c), addr[c]);
+                        acc = chain_step<RED>(acc, pre[c], v, startw & (1u << c));
+                        res[c] = acc;
                     }
+#pragma unroll
+                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], res[c], endw & (1u << c));
                 };
                 for (int c0 = 0; c0 < n; c0 += 32) {
                     if (n - c0 <= 16) batch(std::integral_constant<int, 16>{}, c0);
@@ -524,11 +543,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     a.x = dx * rstd * w.x + b.x; a.y = dy * rstd * w.y + b.y;
                     a.z = dz * rstd * w.z + b.z; a.w = dw * rstd * w.w + b.w;
                 }
-                if (p.out_bf16) {
+                if (p.out_mode == 1) {
                     __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t *>(&lo); pk.y = *reinterpret_cast<uint32_t *>(&hi);
                     reinterpret_cast<uint2 *>(p.out)[(size_t)v * (kD / 4) + lane] = pk;
+                } else if (p.out_mode == 2) {      // fp16 (hi | lo') row: hi halfs at [0, 128), lo' halfs at [128, 256)
+                    __half h0, h1, h2, h3, l0, l1, l2, l3;
+                    const bool ok = split_f16(a.x, h0, l0) & split_f16(a.y, h1, l1) & split_f16(a.z, h2, l2) & split_f16(a.w, h3, l3);
+                    uint2 *row = reinterpret_cast<uint2 *>(p.out) + (size_t)v * (2 * kD / 4);
+                    row[lane] = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                    row[kD / 4 + lane] = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+                    if (!ok && p.status != nullptr) *reinterpret_cast<volatile int32_t *>(p.status) = 1;
                 } else {
                     reinterpret_cast<float4 *>(p.out)[(size_t)v * (kD / 4) + lane] = a;
                 }
@@ -546,16 +572,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
 // =====================================================================================================================
 // packing kernels
 // =====================================================================================================================
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-// x -> (hi, lo') fp16 pair; returns false when |x| is not representable (>= 65504, inf, NaN)
-__device__ __forceinline__ bool split_f16(float x, __half &hi, __half &lo) {
-    hi = __float2half_rn(x);
-    lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
-    return fabsf(x) < 65504.0f;
-}
-
 // fp32 [rows, K] -> rows of 2K fp16: hi[K] | lo'[K].  One thread per 8 consecutive elements (32 bytes in, 2 x 16 bytes out).
 __global__ void __launch_bounds__(256) pack_states_kernel(const float *__restrict__ h, long long rows, int K,
                                                           uint4 *__restrict__ out, int32_t *__restrict__ status) {
@@ -725,7 +741,7 @@ int aggregate(const AggregateArgs &a, cudaStream_t st) {
     p.group_off = a.group_off; p.src_f = a.src_f; p.tl_f = a.tl_f; p.row_ptr = a.row_ptr;
     p.out = a.out; p.num_nodes = (int)a.num_nodes; p.B = a.block_targets;
     p.num_blocks = (int)ceil_div(a.num_nodes, a.block_targets);
-    p.T = a.num_types; p.reduce = a.reduce; p.out_bf16 = a.out_bf16; p.epi = a.epi;
+    p.T = a.num_types; p.reduce = a.reduce; p.out_mode = a.out_mode; p.status = a.status; p.epi = a.epi;
     if (a.nprod == 3) {
         if (a.K == 64) return launch_seg<3, 64>(p, a.use_target, st);
         return launch_seg<3, 128>(p, a.use_target, st);

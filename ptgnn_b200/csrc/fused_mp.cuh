@@ -69,8 +69,9 @@ struct AggregateArgs {
     const int32_t *row_ptr;         // CSR offsets over targets (mean only; may be null otherwise)
     const void *packed_weights;
     Epilogue epi;
-    void *out;                      // [num_nodes, 128] fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1)
-    int out_bf16;
+    void *out;                      // [num_nodes, 128]: out_mode 0 = fp32, 1 = bf16, 2 = packed fp16 (hi | lo') rows of 256 halfs
+    int out_mode;                   //   (2 = what the weights-stationary GRU kernel takes as its A operand)
+    int32_t *status;                // optional: status[0] = 1 if an aggregate is outside the fp16 range (out_mode 2)
 };
 int aggregate(const AggregateArgs &a, cudaStream_t st);
 

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "fused_mp.cuh"
+#include "gru_ws.cuh"
 #include "gemm_simt.cuh"
 #include "layers_tc.cuh"
 #include "reduce.cuh"
@@ -282,7 +283,7 @@ static bool tc_enabled() {
 
 // `fused` layouts (block plan given, dims supported): no [E, D] message buffer; instead the packed (hi | lo') fp16 copy
 // of the source states (Ns rows) and the TMEM-layout edge weights of the fused kernel.
-struct GatedWs { size_t msg, agg, p1, p2, wsplit, grupack, xpack, total; };
+struct GatedWs { size_t msg, agg, p1, p2, wsplit, grupack, xpack, xpack_own, total; };
 static GatedWs gated_ws_layout(int64_t N, int64_t Ns, int64_t E, int T, int H, int D, bool fused_path) {
     GatedWs w{};
     size_t o = 0;
@@ -292,8 +293,9 @@ static GatedWs gated_ws_layout(int64_t N, int64_t Ns, int64_t E, int T, int H, i
     w.p1 = add((size_t)(H / 32 + 1) * 96 * D);
     w.p2 = add((size_t)(H / 32 + 1) * 96 * H);
     w.wsplit = o; o += fused_path ? fused::packed_weight_bytes(3, T, H, 0) : tc::split_edge_weights_bytes(T, D, H);
-    w.grupack = o; o += tc::gru_pack_bytes(H + 32, D);
+    w.grupack = o; o += tc::gru_pack_bytes(H + 32, D) + (fused_path && gruws::supported(3, H, D) ? gruws::pack_bytes(3, H, D) : 0);
     w.xpack = o; o += fused_path ? fused::packed_state_bytes(3, Ns, H) : 0;
+    w.xpack_own = o; o += fused_path ? fused::packed_state_bytes(3, N, H) : 0;   // sharded run (gather_states given): this rank's rows for the GRU
     w.total = o;
     return w;
 }
@@ -331,8 +333,14 @@ static size_t gated_cache_bytes(int T, int H, int D) {
     return tc::split_edge_weights_bytes(T, D, H) + tc::gru_pack_bytes(H, D);
 }
 static bool fused_f32_ok(int H, int D) { return tc_enabled() && fused::supported(3, H, D, 0) && tc::supported_gru(H, D); }
+// PTGNN_B200_GRU=tc selects the round-1 GRU pipeline (3xTF32, streams its weights per tile) behind the fused aggregation
+static bool gru_ws_enabled(int nprod, int H, int D) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PTGNN_B200_GRU"); v = (e && e[0] == 't') ? 0 : 1; }
+    return v == 1 && gruws::supported(nprod, H, D);
+}
 static size_t gated_fused_cache_bytes(int T, int H, int D) {
-    return fused::packed_weight_bytes(3, T, H, 0) + tc::gru_pack_bytes(H, D);
+    return fused::packed_weight_bytes(3, T, H, 0) + (gru_ws_enabled(3, H, D) ? gruws::pack_bytes(3, H, D) : tc::gru_pack_bytes(H, D));
 }
 
 static int gated_forward_impl(const float *node_states, const float *gather_states, int64_t num_nodes, int32_t state_dim,
@@ -400,10 +408,25 @@ static int gated_forward_impl(const float *node_states, const float *gather_stat
         a.nprod = 3; a.src_rows = ws + L.xpack; a.tgt_rows = nullptr; a.num_nodes = num_nodes; a.K = H; a.num_types = num_types;
         a.use_target = 0; a.reduce = reduce; a.block_targets = bp->block_targets; a.group_off = bp->group_off; a.src_f = bp->src_f;
         a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = wsplit; a.epi = fused::Epilogue{PTGNN_ACT_NONE, nullptr, nullptr, 0.0f};
-        a.out = agg; a.out_bf16 = 0;
+        a.status = bp->status;
+        const bool ws_gru = gru_ws_enabled(3, H, D);
+        a.out = agg; a.out_mode = ws_gru ? 2 : 0;
         rc = fused::aggregate(a, st);
         if (rc) return rc;
-        return tc::gru_update(agg, node_states, num_nodes, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, out_states, grupack, pack, st);
+        if (!ws_gru)
+            return tc::gru_update(agg, node_states, num_nodes, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, out_states, grupack, pack, st);
+        // 3. GRUCell, weights-stationary, on the packed aggregate and the packed states (3xFP16)
+        if (pack) {
+            rc = gruws::pack(3, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, grupack, st);
+            if (rc) return rc;
+        }
+        const void *h_rows = ws + L.xpack;
+        if (gather_states != nullptr && gather_states != node_states) {   // sharded run: the packed copy above holds the GATHERED rows; the GRU needs this rank's
+            rc = fused::pack_states(node_states, num_nodes, H, ws + L.xpack_own, bp->status, st);
+            if (rc) return rc;
+            h_rows = ws + L.xpack_own;
+        }
+        return gruws::update(3, agg, h_rows, node_states, num_nodes, H, D, grupack, out_states, st);
     }
 
     // 1. per-edge messages, written at their target-sorted positions
@@ -539,7 +562,7 @@ static int mlp_forward_impl(const float *node_states, const float *gather_states
         a.use_target = ut; a.reduce = reduce; a.block_targets = bp->block_targets; a.group_off = bp->group_off; a.src_f = bp->src_f;
         a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = ws + L.wsplit;
         a.epi = fused::Epilogue{message_activation, ln_weight, ln_bias, ln_eps};
-        a.out = y; a.out_bf16 = 0;
+        a.out = y; a.out_mode = 0; a.status = bp->status;
         rc = fused::aggregate(a, st);
         if (rc) return rc;
     } else {

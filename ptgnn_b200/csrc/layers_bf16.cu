@@ -9,6 +9,7 @@
 
 #include "layers_tc.cuh"
 #include "fused_mp.cuh"
+#include "gru_ws.cuh"
 #include "tc_pipeline_bf16.cuh"
 
 namespace ptgnn {
@@ -464,7 +465,7 @@ static int launch_pipeline(const typename Policy::Params &p, int total_tiles, in
     return PTGNN_OK;
 }
 
-struct WsB { size_t msg, agg, w, p1, p2, bias, total; };
+struct WsB { size_t msg, agg, w, p1, p2, bias, gws, total; };
 static WsB ws_layout(int64_t N, int64_t E, int T, int H, int D) {
     WsB w{};
     size_t o = 0;
@@ -475,6 +476,7 @@ static WsB ws_layout(int64_t N, int64_t E, int T, int H, int D) {
     w.p1 = add((size_t)(H / 32 + 1) * 128 * D);
     w.p2 = add((size_t)(H / 32 + 1) * 128 * H);
     w.bias = add((size_t)H * 8 + 8);
+    w.gws = add(gruws::supported(1, H, D) ? gruws::pack_bytes(1, H, D) / 2 + 8 : 8);   // weights-stationary GRU packing (fused path)
     w.total = o;
     return w;
 }
@@ -583,9 +585,19 @@ static int gated_forward_bf16_impl(const uint16_t *node_states, const uint16_t *
         a.nprod = 1; a.src_rows = hsrc; a.tgt_rows = nullptr; a.num_nodes = num_nodes; a.K = H; a.num_types = num_types;
         a.use_target = 0; a.reduce = reduce; a.block_targets = bp->block_targets; a.group_off = bp->group_off; a.src_f = bp->src_f;
         a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = wb; a.epi = fused::Epilogue{PTGNN_ACT_NONE, nullptr, nullptr, 0.0f};
-        a.out = agg; a.out_bf16 = 1;
+        a.out = agg; a.out_mode = 1; a.status = bp->status;
         rc = fused::aggregate(a, st);
         if (rc) return rc;
+        static const bool ws_gru_on = [] { const char *e = getenv("PTGNN_B200_GRU"); return !(e && e[0] == 't'); }();
+        if (ws_gru_on && gruws::supported(1, H, D)) {
+            // 3. GRUCell, weights-stationary (the gate weights stay in shared memory, only node rows stream)
+            char *gws = wbase + (L.gws - L.w);
+            if (pack) {
+                rc = gruws::pack(1, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, gws, st);
+                if (rc) return rc;
+            }
+            return gruws::update(1, agg, h, h, num_nodes, H, D, gws, out_states, st);
+        }
     } else {
     // 1. messages
     MsgPolicyB::Params mp{};
@@ -759,7 +771,7 @@ static int mlp_forward_bf16_impl(const uint16_t *node_states, const uint16_t *ga
         a.use_target = ut; a.reduce = reduce; a.block_targets = bp->block_targets; a.group_off = bp->group_off; a.src_f = bp->src_f;
         a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = wb;
         a.epi = fused::Epilogue{message_activation, ln_weight, ln_bias, ln_eps};
-        a.out = y; a.out_bf16 = 1;
+        a.out = y; a.out_mode = 1; a.status = bp->status;
         rc = fused::aggregate(a, st);
         if (rc || !dense_weight) return rc;
     } else {

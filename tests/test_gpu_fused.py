@@ -89,7 +89,9 @@ def test_fused_gated_hub_and_isolated_targets():
                                     **gated_oracle_args({k: v.clone().cpu() for k, v in layer.state_dict().items()}))
         with torch.no_grad():
             got = layer(h.cuda(), _dev(adj))
-        assert_close(got, ref, tol=2e-5 if agg == "sum" else 1e-5, what=f"hub {agg}")   # 3000-term sums: allow 2 ulp-ish slack
+        # a 3000-term fp32 sum (|partial sums| ~ 50): the reference's own sequential summation carries ~sqrt(3000) x 2^-24 x 50 =
+        # 1.6e-4 of rounding noise, so agreement to 5e-5 on the hub row is already inside what fp32 defines; max is exact-ish
+        assert_close(got, ref, tol=5e-5 if agg == "sum" else 1e-5, what=f"hub {agg}")
 
 
 @pytest.mark.parametrize("agg", ["sum", "max", "mean"])
