@@ -289,6 +289,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="node-state dtype; f32 is the headline (reference CPU path precision), bf16 = BASELINE.json configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="do not measure the CUDA-graph replay variant of the e2e loop")
+    ap.add_argument("--no-row-shard", action="store_true", help="skip the node-range-split (all-gather) extra measurement")
     ap.add_argument("--profile", action="store_true", help="only the HBM-resident loop (for runs under ncu); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -380,7 +382,9 @@ def main():
         and the D2H of step i-1 overlap the kernels of step i -- what the reference's own background minibatch threads do
         (`ptgnn/baseneuralmodel/abstractneuralmodel.py:348-357`)."""
 
-        def __init__(self):
+        def __init__(self, graphed: bool = False):
+            self.graphed = graphed           # replay GraphNeuralNetwork.capture() graphs (one per input buffer) instead of eager calls
+            self.graphs = [None, None]
             self.h2d, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.h_buf = [torch.empty_like(h_dev) for _ in range(2)]
             self.adj_buf = [[(torch.empty_like(s), torch.empty_like(t)) for s, t in adj_dev] for _ in range(2)]
@@ -408,17 +412,23 @@ def main():
             if not self.prefetched[k]:
                 self._prefetch(k)
             main.wait_event(self.in_ready[k])
-            P.clear_plan_cache()
-            with torch.no_grad():
-                res = gnn(node_data={"input": self.h_buf[k]}, adjacency_lists=list(self.adj_buf[k]), edge_feature_data=[],
-                          node_to_graph_idx=n2g, reference_node_ids={}, reference_node_graph_idx={}, num_graphs=batch.num_graphs)
-            out = res.output_node_representations
+            if self.graphed:
+                if self.graphs[k] is None:      # first use of this buffer pair (inside the warm-up): capture plan + 8 layers
+                    self.graphs[k] = gnn.capture(self.h_buf[k], gnn.expand_adjacency(self.adj_buf[k], n_nodes, dev), n2g)
+                out = self.graphs[k].replay()
+            else:
+                P.clear_plan_cache()
+                with torch.no_grad():
+                    res = gnn(node_data={"input": self.h_buf[k]}, adjacency_lists=list(self.adj_buf[k]), edge_feature_data=[],
+                              node_to_graph_idx=n2g, reference_node_ids={}, reference_node_graph_idx={}, num_graphs=batch.num_graphs)
+                out = res.output_node_representations
             self.compute_done[k].record(main)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(self.compute_done[k])
                 self.out_host[k].copy_(out, non_blocking=True)
                 self.d2h_done[k].record(self.d2h)
-            out.record_stream(self.d2h)
+            if not self.graphed:
+                out.record_stream(self.d2h)
             self.keep[k] = out
             self.prefetched[k] = False
             self._prefetch(1 - k)                               # inputs of the next step
@@ -468,8 +478,20 @@ def main():
     clock_summary = clocks.summary()
     ms_e2e_serial, _ = timed(step_e2e, args.steps, args.warmup)
     pipe = PipelinedE2E()
-    ms_e2e, _ = timed(pipe.step, args.steps, args.warmup, finish=pipe.finish)
-    host_ms_e2e = timed.host_ms
+    ms_e2e_eager, _ = timed(pipe.step, args.steps, args.warmup, finish=pipe.finish)
+    host_ms_eager = timed.host_ms
+    ms_e2e, host_ms_e2e, e2e_mode = ms_e2e_eager, host_ms_eager, "eager"
+    if not args.no_graphs:
+        try:
+            gpipe = PipelinedE2E(graphed=True)
+            ms_g, _ = timed(gpipe.step, args.steps, max(args.warmup, 4), finish=gpipe.finish)
+            if ms_g < ms_e2e_eager:
+                ms_e2e, host_ms_e2e, e2e_mode = ms_g, timed.host_ms, "cuda-graph"
+            graph_info = {"ms_per_step": ms_g, "host_enqueue_ms_per_step": timed.host_ms}
+        except Exception as exc:     # capture is an optimisation of the host side only: report, never hide
+            graph_info = {"error": repr(exc)[:300]}
+    else:
+        graph_info = None
 
     total_edges = E * world
     value = total_edges * NUM_LAYERS / (ms_step * 1e-3)
@@ -576,6 +598,41 @@ def main():
                       "frac": b_min / (layer_ms * 1e-3) / 1e9 / peak, "ms_per_layer": layer_ms,
                       "nodes_per_sec_per_layer": n_nodes * world / (layer_ms * 1e-3)}
 
+    # ---- BASELINE.json configs[3] extras (kept out of `value`): (1) the node-range split of ONE connected graph of the same size
+    # (N = 204,800, T = 17, E = 1,105,920; strong scaling) with the per-layer NCCL all-gather of the state shards, in this
+    # run's dtype; (2) the exposed time of those all-gathers alone.  At world == 1 the all-gather is a no-op.
+    row_shard = None
+    if args.workload == "graph2class" and not args.no_row_shard:
+        from ptgnn_b200 import sharding
+        from ptgnn_b200.synthetic import single_random_graph
+
+        g1 = single_random_graph(n_nodes, sum(int(a[0].shape[0]) for a in batch.adjacency_lists), len(batch.adjacency_lists), seed=77)
+        full_adj = [(s.to(dev), t.to(dev)) for s, t in g1.adjacency_lists]
+        full_adj = list(full_adj) + [(t, s) for s, t in full_adj] + [(ident, ident)]
+        shard = sharding.row_shard(n_nodes, full_adj, world, rank)
+        loop = sharding.RowShardedLayerLoop(shard)
+        own = h_dev[shard.lo:shard.hi].contiguous()
+        layer_fns = [lambda o, f, a, L=L: L(o, a, gather_states=f if world > 1 else None) for L in gnn.message_passing_layers]
+
+        def step_rows():
+            P.clear_plan_cache()
+            with torch.no_grad():
+                return loop.run(own, layer_fns)
+
+        def step_allgather_only():
+            with torch.no_grad():
+                for _ in range(NUM_LAYERS):
+                    loop.all_gather_states(own)
+
+        ms_rows, _ = timed(step_rows, args.steps, args.warmup)
+        ms_ag, _ = timed(step_allgather_only, args.steps, args.warmup) if world > 1 else (0.0, 0)
+        E1 = sum(int(a[0].shape[0]) for a in full_adj)
+        row_shard = {"workload": f"one connected random graph, N={n_nodes}, T={len(full_adj)}, E={E1}, node-range split over {world} rank(s), "
+                                 f"one all_gather_into_tensor of the [N/P, {HIDDEN}] state shards per layer (NCCL)",
+                     "value": E1 * NUM_LAYERS / (ms_rows * 1e-3), "unit": "edges/s", "ms_per_step": ms_rows, "scaling": "strong",
+                     "allgather_ms_per_step": ms_ag, "allgather_bytes_per_layer": n_nodes * HIDDEN * esz,
+                     "note": "the all-gathers are not overlapped with compute: allgather_ms_per_step is fully exposed"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.dtype == "f32":
         r = cpu_reference_run(batch, gnn, args.agg, steps=3, warmup=1, budget_s=25.0)
@@ -588,11 +645,15 @@ def main():
             "data": "synthetic", "config": config, "clocks": clock_summary,
             "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": "pipelined over steps on 3 streams: H2D(i+1) and D2H(i-1) overlap the kernels of step i; every step copies "
-                            "its inputs from pinned host memory and its result back",
+                            "its inputs from pinned host memory and its result back; layer loop = " + e2e_mode +
+                            (" (GraphNeuralNetwork.capture: plan build + 8 layers replayed as one CUDA graph)" if e2e_mode == "cuda-graph" else ""),
+                    "eager_pipelined": {"value": total_edges * NUM_LAYERS / (ms_e2e_eager * 1e-3), "ms_per_step": ms_e2e_eager,
+                                        "host_enqueue_ms_per_step": host_ms_eager},
+                    "cuda_graph_pipelined": graph_info,
                     "serial_value": total_edges * NUM_LAYERS / (ms_e2e_serial * 1e-3), "serial_ms_per_step": ms_e2e_serial,
                     "host_enqueue_ms_per_step": host_ms_e2e},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "cpu_baseline": cpu, "row_shard": row_shard,
         }
         print(json.dumps(line))
     if world > 1:

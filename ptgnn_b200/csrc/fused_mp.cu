@@ -130,24 +130,16 @@ struct StepGen {
     }
 };
 
-// One accumulator column of the epilogue: returns op(start ? pre : prev, v).  Two predicated ops instead of select + op keep the
-// serial chain at one ALU latency per column.  The result goes to a FRESH register (the caller keeps all 32 of a batch and
-// stores them afterwards): storing the running value straight from the chain register makes every following column wait for
-// the store to read it (short-scoreboard WAR stall, ~20 cycles per column -- measured: the epilogue was the kernel's limit).
+// t = op(prev, v) unless the column starts a segment: ONE predicated instruction (a select would put two ALU latencies per
+// column on the serial chain)
 template <int RED>
-__device__ __forceinline__ float chain_step(float prev, float pre, float v, uint32_t start_bit) {
-    float r;
-    if (RED == PTGNN_REDUCE_MAX) {
-        asm("{\n\t.reg .pred ps;\n\tsetp.ne.u32 ps, %4, 0;\n\t@ps max.f32 %0, %1, %2;\n\t@!ps max.f32 %0, %3, %2;\n\t}"
-            : "=f"(r) : "f"(pre), "f"(v), "f"(prev), "r"(start_bit));
-    } else if (RED == PTGNN_REDUCE_MIN) {
-        asm("{\n\t.reg .pred ps;\n\tsetp.ne.u32 ps, %4, 0;\n\t@ps min.f32 %0, %1, %2;\n\t@!ps min.f32 %0, %3, %2;\n\t}"
-            : "=f"(r) : "f"(pre), "f"(v), "f"(prev), "r"(start_bit));
-    } else {
-        asm("{\n\t.reg .pred ps;\n\tsetp.ne.u32 ps, %4, 0;\n\t@ps add.f32 %0, %1, %2;\n\t@!ps add.f32 %0, %3, %2;\n\t}"
-            : "=f"(r) : "f"(pre), "f"(v), "f"(prev), "r"(start_bit));
-    }
-    return r;
+__device__ __forceinline__ void continue_segment(float &t, float prev, float v, uint32_t start_bit) {
+    if (RED == PTGNN_REDUCE_MAX)
+        asm("{\n\t.reg .pred pc;\n\tsetp.eq.u32 pc, %3, 0;\n\t@pc max.f32 %0, %1, %2;\n\t}" : "+f"(t) : "f"(prev), "f"(v), "r"(start_bit));
+    else if (RED == PTGNN_REDUCE_MIN)
+        asm("{\n\t.reg .pred pc;\n\tsetp.eq.u32 pc, %3, 0;\n\t@pc min.f32 %0, %1, %2;\n\t}" : "+f"(t) : "f"(prev), "f"(v), "r"(start_bit));
+    else
+        asm("{\n\t.reg .pred pc;\n\tsetp.eq.u32 pc, %3, 0;\n\t@pc add.f32 %0, %1, %2;\n\t}" : "+f"(t) : "f"(prev), "f"(v), "r"(start_bit));
 }
 __device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, uint32_t bit) {
     asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.u32 pe, %2, 0;\n\t@pe st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v), "r"(bit) : "memory");
@@ -172,8 +164,8 @@ template <int RED> __device__ __forceinline__ float red_identity() {
     return RED == PTGNN_REDUCE_MAX ? -FLT_MAX : (RED == PTGNN_REDUCE_MIN ? FLT_MAX : 0.0f);
 }
 template <int RED> __device__ __forceinline__ float red_op(float a, float m) {
-    if (RED == PTGNN_REDUCE_MAX) return m > a ? m : a;      // strict compare: NaN never wins (torch_scatter)
-    if (RED == PTGNN_REDUCE_MIN) return m < a ? m : a;
+    if (RED == PTGNN_REDUCE_MAX) return fmaxf(a, m);        // one FMNMX; a NaN message never wins (torch_scatter's strict compare)
+    if (RED == PTGNN_REDUCE_MIN) return fminf(a, m);
     return a + m;
 }
 
@@ -484,17 +476,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
 #pragma unroll
                     for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
                     tc::tmem_ld_wait();
-                    float res[W];
+                    // t[c] = op(pre[c], v[c]) for every column (independent); a column that CONTINUES a segment (rare: most
+                    // (target, type) segments hold one edge) then overwrites it with op(t[c-1], v[c]) -- a predicated op, in
+                    // column order, so a target's messages are still combined one by one in plan order
+                    float t[W];
 #pragma unroll
                     for (int c = 0; c < W; ++c) {
                         float v = __uint_as_float(vm[c]);
                         if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
                         else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
-                        acc = chain_step<RED>(acc, pre[c], v, startw & (1u << c));
-                        res[c] = acc;
+                        vm[c] = __float_as_uint(v);
+                        t[c] = red_op<RED>(pre[c], v);
                     }
+                    continue_segment<RED>(t[0], acc, __uint_as_float(vm[0]), startw & 1u);
 #pragma unroll
-                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], res[c], endw & (1u << c));
+                    for (int c = 1; c < W; ++c) continue_segment<RED>(t[c], t[c - 1], __uint_as_float(vm[c]), startw & (1u << c));
+                    acc = t[W - 1];
+#pragma unroll
+                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], t[c], endw & (1u << c));
                 };
                 for (int c0 = 0; c0 < n; c0 += 32) {
                     if (n - c0 <= 16) batch(std::integral_constant<int, 16>{}, c0);

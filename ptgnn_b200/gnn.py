@@ -11,7 +11,7 @@ from typing import Any, Dict, List, NamedTuple, Optional, Tuple
 import torch
 from torch import nn
 
-from .edgeplan import EdgePlan, plan_for, shared_plan
+from .edgeplan import EdgePlan, clear_plan_cache, plan_for, shared_plan
 from .messagepassing import AbstractMessagePassingLayer
 
 
@@ -146,6 +146,15 @@ class GraphNeuralNetwork(nn.Module):
             node_representations = torch.cat(all_states, dim=-1)
         return node_representations
 
+    def capture(self, node_states: torch.Tensor, adjacency_lists: List[Tuple[torch.Tensor, torch.Tensor]],
+                node_to_graph_idx: Optional[torch.Tensor] = None, return_all_states: bool = False) -> "GraphedLayerLoop":
+        """CUDA-graph the layer loop (edge plan + all layers) for FIXED shapes: the returned object replays it with one launch.
+        ``node_states`` / ``adjacency_lists`` (already expanded, see ``expand_adjacency``) are the static input buffers -- refill
+        them in place (e.g. with ``copy_`` from pinned host memory) and call ``replay()``.  The per-type edge COUNTS are frozen at
+        capture; the edge contents, the node states and -- because the plan is rebuilt inside the graph -- the graph structure
+        are whatever the buffers hold at replay time.  Parameters must not change between capture and replay (eval mode)."""
+        return GraphedLayerLoop(self, node_states, adjacency_lists, node_to_graph_idx, return_all_states)
+
     def expand_adjacency(self, adjacency_lists, num_nodes: int, device) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         """Backward + self edge lists (graphneuralnetwork.py:172-186) as a NEW list."""
         expanded = list(adjacency_lists)
@@ -188,3 +197,36 @@ class GraphNeuralNetwork(nn.Module):
             node_graph_idx_reference=reference_node_graph_idx,
             num_graphs=num_graphs,
         )
+
+
+class GraphedLayerLoop:
+    """``GraphNeuralNetwork.gnn`` captured into one CUDA graph (see ``GraphNeuralNetwork.capture``).  Replaces ~50 kernel
+    launches and ~10 ctypes calls per minibatch by one ``cudaGraphLaunch``: what the reference would get from
+    ``torch.cuda.graphs`` around its own loop, here including the plan build."""
+
+    def __init__(self, gnn: GraphNeuralNetwork, node_states, adjacency_lists, node_to_graph_idx, return_all_states: bool):
+        if gnn.training:
+            raise RuntimeError("capture() needs eval mode (the derived-weight caches are only trusted there)")
+        self.node_states, self.adjacency_lists = node_states, list(adjacency_lists)
+        self._gnn = gnn
+        dev = node_states.device
+        run = lambda: gnn.gnn(node_states, self.adjacency_lists, None, node_to_graph_idx, {}, {}, return_all_states=return_all_states)  # noqa: E731
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():     # warm-up outside the graph: fills weight caches and allocator pools
+            for _ in range(2):
+                clear_plan_cache()
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        clear_plan_cache()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.output = run()
+        self._plan = plan_for(self.adjacency_lists, node_states.shape[0])    # built during capture; keeps its buffers and status words
+        clear_plan_cache()
+
+    def replay(self) -> torch.Tensor:
+        self._plan.poll()          # errors the previous replay's kernels reported (bad indices, fp16-range overflow)
+        self.graph.replay()
+        return self.output

@@ -232,3 +232,35 @@ def test_two_devices_in_one_process():
                 outs.append(layer(h.to(dev), [(s.to(dev), t.to(dev)) for s, t in adj]).cpu())
             os.environ.pop("PTGNN_B200_FUSED")
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+# ---- 8. CUDA-graph capture of the layer loop -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_captured_layer_loop_matches_eager_and_follows_its_buffers(dtype):
+    import ptgnn_b200 as P
+
+    gen = torch.Generator().manual_seed(21)
+    torch.manual_seed(21)
+    n, H = 5000, 128
+    raw = [(torch.randint(0, n, (7000,), generator=gen), torch.randint(0, n, (7000,), generator=gen)),
+           (torch.randint(0, n, (3000,), generator=gen), torch.randint(0, n, (3000,), generator=gen))]
+    layers = [P.GatedMessagePassingLayer(H, H, 5, "sum"), P.GatedMessagePassingLayer(H, H, 5, "max")]
+    gnn = P.GraphNeuralNetwork(layers, _Embed(), True, True).cuda().eval()
+    h_buf = torch.randn(n, H, generator=gen).to(dtype).cuda()
+    adj_buf = gnn.expand_adjacency(_dev(raw), n, "cuda")
+    graphed = gnn.capture(h_buf, adj_buf)
+    with torch.no_grad():
+        eager = gnn.gnn(h_buf, adj_buf, None, None, {}, {})
+    assert torch.equal(graphed.replay(), eager)
+    # new minibatch of the same shape: refill the static buffers in place (states AND edges), replay
+    h2 = torch.randn(n, H, generator=gen).to(dtype).cuda()
+    raw2 = [(torch.randint(0, n, (7000,), generator=gen).cuda(), torch.randint(0, n, (7000,), generator=gen).cuda()),
+            (torch.randint(0, n, (3000,), generator=gen).cuda(), torch.randint(0, n, (3000,), generator=gen).cuda())]
+    h_buf.copy_(h2)
+    for (bs, bt), (s, t) in zip(adj_buf[:2], raw2):
+        bs.copy_(s); bt.copy_(t)       # the backward-edge entries of adj_buf alias these tensors
+    out2 = graphed.replay().clone()
+    P.clear_plan_cache()
+    with torch.no_grad():
+        eager2 = gnn.gnn(h2, gnn.expand_adjacency(raw2, n, "cuda"), None, None, {}, {})
+    assert torch.equal(out2, eager2)

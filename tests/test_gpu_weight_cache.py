@@ -29,7 +29,10 @@ def test_weight_cache_reuse_and_invalidation(dtype):
         out_hit = layer(h, adj)             # reuses them
         l2 = N.launch_count()
     assert torch.equal(out_fill, out_hit)
-    assert (l2 - l1) == (l1 - l0) - 3, "the cached call must skip exactly the three weight-derivation launches"
+    # fused path: edge-weight packing + GRU gate-block packing (2 launches); round-1 path (PTGNN_B200_FUSED=0): 3 launches
+    import os
+    derive = 3 if os.environ.get("PTGNN_B200_FUSED", "1") == "0" else 2
+    assert (l2 - l1) == (l1 - l0) - derive, "the cached call must skip exactly the weight-derivation launches"
 
     # in-place update (what load_state_dict / an optimiser step does): the cache must not be used
     with torch.no_grad():
