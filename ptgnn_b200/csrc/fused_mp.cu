@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     }
                 }
             };
-            auto finish_meta = [&]() {                 // column metadata of `nxt` for the epilogue (columns g and g + 64)
-                if (!has_nxt || nxt.seg != 0) return;
+            auto finish_meta = [&](const Step &st) {   // column metadata of step `st` for the epilogue (columns g and g + 64),
+                if (st.seg != 0) return;               // from the tl_a / tl_b loads issued one whole step earlier
                 Meta *m = &meta_ring[sgc % META_RING];
 #pragma unroll
                 for (int half = 0; half < NMAX / 64; ++half) {
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     const uint32_t word = __ballot_sync(0xffffffffu, end);
                     if (lane == 0) m->endmask[c >> 5] = word;
                 }
-                if (g == 0) m->n = nxt.n;
+                if (g == 0) m->n = st.n;
                 ++sgc;
             };
             auto issue_next = [&]() {                  // issue the copies of `nxt`, prefetch the step after it
@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 int idx[NMAX / 8];
 #pragma unroll
                 for (int i = 0; i < NMAX / 8; ++i) idx[i] = idx_nxt[i];
-                fetch();
+                finish_meta(cur);                      // consumes the loads of the PREVIOUS call
+                fetch();                               // loads for the following step: in flight during the copies below
                 const uint32_t slot = c_issue % NUM_SLOTS;
                 mbar_wait(&x_empty[slot], ((c_issue / NUM_SLOTS) & 1) ^ 1);
                 const unsigned char *rows = cur.seg == 0 ? p.src_rows : p.tgt_rows;
@@ -402,10 +403,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     }
                 }
                 ++c_issue;
-                finish_meta();
             };
             fetch();
-            finish_meta();
             bool more = has_nxt;
 #pragma unroll
             for (int i = 0; i < LOOKAHEAD; ++i) {
