@@ -276,6 +276,31 @@ int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *node_states, c
                                  void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stand-alone pieces of the layers, for the configurations the fused entry points do not cover.
+ *   linear:        out[rows, out_dim] = act(x W^T + b)  -- one `nn.Linear` (+ activation) of `MLP.forward` (mlp.py:79-80) or of an
+ *                  Mlp layer's dense update (mlpmessagepassing.py:116); fp32-exact on the tensor cores when the dims fit.
+ *   edge_messages: messages[out_row[e]] = W_{t(e)} [source_states[src32[e]] ; target_states[tgt32[e]]]  for every edge e in
+ *                  cat(types) order (gatedmessagepassing.py:54-60, mlpmessagepassing.py:88-98) -- the [E, D] tensor that a module
+ *                  aggregator (`AbstractMessageAggregation`, e.g. PNA: pna_aggregation.py:27-56) or a second MLP layer consumes.
+ *                  out_row = the plan's `pos` (target-sorted rows) or the identity (edge order, as the reference lays them out).
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptgnn_b200_linear_workspace_bytes(int32_t in_dim, int32_t out_dim);
+int ptgnn_b200_linear_f32(const float *x, int64_t rows, int32_t in_dim, const float *weight /*[out_dim, in_dim]*/,
+                          const float *bias /* NULL: none */, int32_t out_dim, int32_t activation, float *out, void *workspace,
+                          size_t workspace_bytes, void *stream);
+/*   grucell:       out = nn.GRUCell(input [rows, input_dim], hidden [rows, state_dim])  (gatedmessagepassing.py:69) */
+size_t ptgnn_b200_grucell_workspace_bytes(int32_t state_dim, int32_t input_dim);
+int ptgnn_b200_grucell_f32(const float *input, const float *hidden, int64_t rows, int32_t state_dim, int32_t input_dim,
+                           const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, float *out, void *workspace,
+                           size_t workspace_bytes, void *stream);
+size_t ptgnn_b200_edge_messages_workspace_bytes(int32_t num_types, int32_t in_dim, int32_t message_dim, int32_t use_target_state);
+int ptgnn_b200_edge_messages_f32(const float *source_states, const float *target_states /* rows tgt32 indexes; NULL if unused */,
+                                 int32_t in_dim, int32_t message_dim, int32_t num_types, const int64_t *type_off /*[host]*/,
+                                 const int32_t *src32, const int32_t *tgt32, const int32_t *out_row,
+                                 const float *const *edge_weights /*[host] T device pointers*/, int32_t use_target_state,
+                                 float *messages, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry point (used for the end-to-end measurement): all pointers are HOST
  * memory; copies inputs to the device, builds the plan, runs `num_layers` GatedMessagePassingLayers
  * (layer l uses weight set l; pass the same pointers to share weights), copies the final states back

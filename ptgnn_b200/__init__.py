@@ -5,6 +5,7 @@ the ``GraphNeuralNetwork`` layer loop and the ``torch_scatter.scatter`` boundary
 own ``nn.Module`` API.  The arithmetic lives in ``libptgnn_b200.so`` (C ABI: ``include/ptgnn_b200.h``); this package
 is the host-side mirror of the reference interface.  There is no CPU / PyTorch fallback.
 """
+from .aggregation import PnaMessageAggregation
 from .edgeplan import EdgePlan, clear_plan_cache, plan_for
 from .gnn import GnnOutput, GraphNeuralNetwork
 from .messagepassing import (
@@ -19,7 +20,7 @@ from .scatter import scatter, scatter_add, scatter_max, scatter_mean, scatter_mi
 
 __all__ = [
     "EdgePlan", "plan_for", "clear_plan_cache", "GnnOutput", "GraphNeuralNetwork", "MLP", "AbstractMessageAggregation",
-    "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "MeanResidualLayer",
+    "PnaMessageAggregation", "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "MeanResidualLayer",
     "ConcatResidualLayer", "LinearResidualLayer", "scatter", "scatter_add",
     "scatter_sum", "scatter_mean", "scatter_max", "scatter_min",
 ]

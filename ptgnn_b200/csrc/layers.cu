@@ -283,6 +283,34 @@ static bool tc_enabled() {
 
 // `fused` layouts (block plan given, dims supported): no [E, D] message buffer; instead the packed (hi | lo') fp16 copy
 // of the source states (Ns rows) and the TMEM-layout edge weights of the fused kernel.
+// out = act(y W^T + b): tensor cores (3xTF32) when the dims fit the tiles, FFMA tiles otherwise.  scratch >= tc::dense_split_bytes.
+static int dense_any(const float *y, int64_t rows, int D, const float *W, const float *bias, int out_dim, int act, float *out,
+                     void *scratch, cudaStream_t st) {
+    if (tc_enabled() && tc::supported_dense(D, out_dim)) return tc::dense_update(y, rows, D, W, bias, out_dim, act, out, scratch, st);
+    int rc;
+    if (out_dim <= 64) {
+        using Tile = GemmTile<4>;
+        rc = set_smem(dense_update_kernel<4>, Tile::SMEM_BYTES);
+        if (rc) return rc;
+        dim3 grid((unsigned)ceil_div(rows, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
+        {
+            TimedScope timed__(PTGNN_KERNEL_DENSE, st);
+            dense_update_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)rows, D, W, bias, out_dim, act, out);
+        }
+    } else {
+        using Tile = GemmTile<8>;
+        rc = set_smem(dense_update_kernel<8>, Tile::SMEM_BYTES);
+        if (rc) return rc;
+        dim3 grid((unsigned)ceil_div(rows, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
+        {
+            TimedScope timed__(PTGNN_KERNEL_DENSE, st);
+            dense_update_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)rows, D, W, bias, out_dim, act, out);
+        }
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
 struct GatedWs { size_t msg, agg, p1, p2, wsplit, grupack, xpack, xpack_own, total; };
 static GatedWs gated_ws_layout(int64_t N, int64_t Ns, int64_t E, int T, int H, int D, bool fused_path) {
     GatedWs w{};
@@ -579,33 +607,7 @@ static int mlp_forward_impl(const float *node_states, const float *gather_states
         if (rc) return rc;
     }
     if (!dense_weight) return PTGNN_OK;
-    if (tc_enabled() && tc::supported_dense(D, out_dim)) {
-        return tc::dense_update(y, num_nodes, D, dense_weight, dense_bias, out_dim, dense_activation, out_states,
-                                ws + L.dsplit, st);
-    }
-    if (out_dim <= 64) {
-        using Tile = GemmTile<4>;
-        rc = set_smem(dense_update_kernel<4>, Tile::SMEM_BYTES);
-        if (rc) return rc;
-        dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
-        {
-            TimedScope timed__(PTGNN_KERNEL_DENSE, st);
-            dense_update_kernel<4><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight, dense_bias,
-                                                                                  out_dim, dense_activation, out_states);
-        }
-    } else {
-        using Tile = GemmTile<8>;
-        rc = set_smem(dense_update_kernel<8>, Tile::SMEM_BYTES);
-        if (rc) return rc;
-        dim3 grid((unsigned)ceil_div(num_nodes, GEMM_BM), (unsigned)ceil_div(out_dim, Tile::BN));
-        {
-            TimedScope timed__(PTGNN_KERNEL_DENSE, st);
-            dense_update_kernel<8><<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(y, (int)num_nodes, D, dense_weight, dense_bias,
-                                                                                  out_dim, dense_activation, out_states);
-        }
-    }
-    PTGNN_LAUNCHED();
-    return PTGNN_OK;
+    return dense_any(y, num_nodes, D, dense_weight, dense_bias, out_dim, dense_activation, out_states, ws + L.dsplit, st);
 }
 
 extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
@@ -709,4 +711,91 @@ extern "C" int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *nod
                             use_target_state, reduce, message_activation, ln_weight, ln_bias, ln_eps, dense_weight, dense_bias,
                             dense_activation, static_cast<float *>(out_states), workspace, workspace_bytes, stream, block_plan,
                             num_source_nodes);
+}
+
+/* ---- stand-alone pieces (MLP.forward, message MLPs with hidden layers, module aggregators) -------------------------------------- */
+extern "C" size_t ptgnn_b200_linear_workspace_bytes(int32_t in_dim, int32_t out_dim) {
+    if (in_dim <= 0 || out_dim <= 0) return 0;
+    return tc::dense_split_bytes(out_dim, in_dim) + 256;
+}
+extern "C" int ptgnn_b200_linear_f32(const float *x, int64_t rows, int32_t in_dim, const float *weight, const float *bias,
+                                     int32_t out_dim, int32_t activation, float *out, void *workspace, size_t workspace_bytes,
+                                     void *stream) {
+    PTGNN_CHECK_ARG(rows >= 0 && rows < INT32_MAX, "linear: rows out of range");
+    PTGNN_CHECK_ARG(in_dim > 0 && in_dim % 4 == 0 && out_dim > 0 && out_dim % 4 == 0 && in_dim <= 4096 && out_dim <= 4096,
+                    "linear: dims %d -> %d must be multiples of 4 (<= 4096)", in_dim, out_dim);
+    PTGNN_CHECK_ARG(activation >= PTGNN_ACT_NONE && activation <= PTGNN_ACT_RELU, "linear: bad activation %d", activation);
+    if (rows == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(x && weight && out, "linear: null pointer");
+    if (workspace_bytes < ptgnn_b200_linear_workspace_bytes(in_dim, out_dim) || !workspace) {
+        set_error("linear: workspace too small");
+        return PTGNN_E_WORKSPACE;
+    }
+    return dense_any(x, rows, in_dim, weight, bias, out_dim, activation, out, workspace, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t ptgnn_b200_edge_messages_workspace_bytes(int32_t num_types, int32_t in_dim, int32_t message_dim, int32_t use_target_state) {
+    if (num_types < 0 || in_dim <= 0 || message_dim <= 0) return 0;
+    return tc::split_edge_weights_bytes(num_types, message_dim, use_target_state ? 2 * in_dim : in_dim) + 256;
+}
+extern "C" int ptgnn_b200_edge_messages_f32(const float *source_states, const float *target_states, int32_t in_dim, int32_t message_dim,
+                                            int32_t num_types, const int64_t *type_off, const int32_t *src32, const int32_t *tgt32,
+                                            const int32_t *out_row, const float *const *edge_weights, int32_t use_target_state,
+                                            float *messages, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && type_off, "edge_messages: bad num_types=%d", num_types);
+    const int64_t E = type_off[num_types];
+    int rc = check_layer_dims("edge_messages", 0, E, in_dim, message_dim);
+    if (rc) return rc;
+    if (E == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(source_states && src32 && out_row && edge_weights && messages && (!use_target_state || (target_states && tgt32)),
+                    "edge_messages: null pointer");
+    if (workspace_bytes < ptgnn_b200_edge_messages_workspace_bytes(num_types, in_dim, message_dim, use_target_state) || !workspace) {
+        set_error("edge_messages: workspace too small");
+        return PTGNN_E_WORKSPACE;
+    }
+    const int ut = use_target_state ? 1 : 0;
+    if (tc_enabled() && tc::supported_message(in_dim, message_dim))
+        return tc::edge_messages(source_states, target_states, in_dim, message_dim, ut, num_types, type_off, edge_weights, src32, tgt32,
+                                 out_row, messages, workspace, true, st);
+    return launch_edge_messages(source_states, target_states, in_dim, message_dim, ut, num_types, type_off, edge_weights, src32, tgt32,
+                                out_row, messages, st);
+}
+
+extern "C" size_t ptgnn_b200_grucell_workspace_bytes(int32_t state_dim, int32_t input_dim) {
+    if (state_dim <= 0 || input_dim <= 0) return 0;
+    return ws_slice((size_t)(state_dim / 32 + 1) * 96 * input_dim, 4) + ws_slice((size_t)(state_dim / 32 + 1) * 96 * state_dim, 4) +
+           tc::gru_pack_bytes(state_dim + 32, input_dim) + 256;
+}
+extern "C" int ptgnn_b200_grucell_f32(const float *input, const float *hidden, int64_t rows, int32_t state_dim, int32_t input_dim,
+                                      const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, float *out,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int H = state_dim, D = input_dim;
+    int rc = check_layer_dims("grucell", rows, 0, H, D);
+    if (rc) return rc;
+    if (H % 32 != 0) { set_error("grucell: state dim %d must be a multiple of 32", H); return PTGNN_E_UNSUPPORTED; }
+    if (rows == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(input && hidden && w_ih && w_hh && b_ih && b_hh && out, "grucell: null pointer");
+    if (workspace_bytes < ptgnn_b200_grucell_workspace_bytes(H, D) || !workspace) { set_error("grucell: workspace too small"); return PTGNN_E_WORKSPACE; }
+    char *ws = static_cast<char *>(workspace);
+    const size_t o1 = ws_slice((size_t)(H / 32 + 1) * 96 * D, 4), o2 = ws_slice((size_t)(H / 32 + 1) * 96 * H, 4);
+    if (tc_enabled() && tc::supported_gru(H, D))
+        return tc::gru_update(input, hidden, rows, H, D, w_ih, w_hh, b_ih, b_hh, out, ws + o1 + o2, true, st);
+    float *P1 = reinterpret_cast<float *>(ws), *P2 = reinterpret_cast<float *>(ws + o1);
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        pack_gru_weights_kernel<<<148, 256, 0, st>>>(w_ih, w_hh, H, D, P1, P2);
+    }
+    PTGNN_LAUNCHED();
+    using Tile = GemmTile<6>;
+    rc = set_smem(gru_update_kernel, Tile::SMEM_BYTES);
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(rows, GEMM_BM), H / 32);
+    {
+        TimedScope timed__(PTGNN_KERNEL_GRU, st);
+        gru_update_kernel<<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(input, hidden, (int)rows, H, D, P1, P2, b_ih, b_hh, out);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
 }

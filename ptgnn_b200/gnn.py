@@ -127,7 +127,17 @@ class GraphNeuralNetwork(nn.Module):
         plan: Optional[EdgePlan] = None,
     ) -> torch.Tensor:
         if self.__edge_dropout_rate > 0 and self.training:
-            raise NotImplementedError("training-mode edge dropout has no native kernel (forward-only round)")
+            # graphneuralnetwork.py:105-119: Bernoulli keep-mask per edge (device-side index bookkeeping; a new plan is built
+            # for the surviving edges, so this also invalidates any plan handed in)
+            kept_adj, kept_feats = [], []
+            feats_in = edge_feature_embeddings if edge_feature_embeddings is not None else [None] * len(adjacency_lists)
+            for (src, tgt), feats in zip(adjacency_lists, feats_in):
+                mask = torch.rand_like(src, dtype=torch.float32) > self.__edge_dropout_rate
+                kept_adj.append((src.masked_select(mask), tgt.masked_select(mask)))
+                kept_feats.append(None if feats is None else feats[mask])
+            adjacency_lists = kept_adj
+            edge_feature_embeddings = kept_feats if edge_feature_embeddings is not None else None
+            plan = None
         if node_representations.is_cuda:
             plan = plan_for(adjacency_lists, node_representations.shape[0], plan)
         all_states = [node_representations]
@@ -180,10 +190,15 @@ class GraphNeuralNetwork(nn.Module):
         initial = self.__node_embedder(**node_data)
         device = node_to_graph_idx.device
         num_nodes = node_to_graph_idx.shape[0]
-        if self.__edge_feature_embedder is not None:
-            raise NotImplementedError("edge feature embedders have no native kernel yet (SURVEY.md §8 row f-4)")
         expanded = self.expand_adjacency(adjacency_lists, num_nodes, device)
-        edge_features = [torch.empty(src.shape[0], 0, device=device) for src, _ in expanded]
+        if self.__edge_feature_embedder is None:
+            edge_features = [torch.empty(src.shape[0], 0, device=device) for src, _ in expanded]
+        else:   # graphneuralnetwork.py:167-186: embed per raw type, reuse for the backward types, zeros for the self edges
+            edge_features = [self.__edge_feature_embedder(**edge_data) for edge_data in edge_feature_data]
+            if self.__introduce_backwards_edges:
+                edge_features = edge_features + list(edge_features)
+            if self.__add_self_edges:
+                edge_features.append(torch.zeros(num_nodes, edge_features[-1].shape[-1], device=device))
         output = self.gnn(initial, expanded, edge_features, node_to_graph_idx, reference_node_ids,
                           reference_node_graph_idx, **kwargs)
         self.__num_edges += sum(src.shape[0] for src, _ in expanded)

@@ -195,11 +195,12 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         assert len(adjacency_lists) == len(linears), "one adjacency list per edge type is required"
         if self.training and self.__dropout.p > 0:
             raise NotImplementedError("training-mode dropout has no native kernel (forward-only round)")
-        if self.__edge_feature_dimension != 0:
-            raise NotImplementedError("edge features (F > 0) have no native kernel yet (SURVEY.md §8 row f-4)")
-        _check_no_edge_features(edge_features)
+        if self.__edge_feature_dimension == 0:
+            _check_no_edge_features(edge_features)
         _refuse_autograd(self, node_states)
         reduce = _reduce_code(self.__aggregation_fn)
+        if self.__edge_feature_dimension != 0:
+            return self._forward_with_edge_features(node_states, adjacency_lists, edge_features, gather_states, reduce)
 
         state_dtype = node_states.dtype if node_states.dtype == torch.bfloat16 else torch.float32
         _check_states(node_states, self.__state_dimension, "GatedMessagePassingLayer")
@@ -269,6 +270,26 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         N.check(rc, "ptgnn_b200_gated_forward_cached_f32")
         self._weight_cache_filled("f32", h.device)
         return out
+
+    def _forward_with_edge_features(self, node_states, adjacency_lists, edge_features, gather_states, reduce: int) -> torch.Tensor:
+        """F > 0 (gatedmessagepassing.py:59: ``cat([h_src, f_e])`` into the per-type Linear): composed from the stand-alone native
+        pieces -- see ptgnn_b200/composed.py.  fp32 states only."""
+        from . import composed as C
+
+        if node_states.dtype != torch.float32:
+            raise NotImplementedError("edge features with bf16 states have no native kernel")
+        _check_states(node_states, self.__state_dimension, "GatedMessagePassingLayer")
+        h = N.require_cuda(node_states, "node_states", torch.float32)
+        gsrc = h if gather_states is None else N.require_cuda(gather_states, "gather_states", torch.float32)
+        plan = self._plan(adjacency_lists, h.shape[0], None if gather_states is None else gsrc.shape[0])
+        H, Fd = self.__state_dimension, self.__edge_feature_dimension
+        weights = [lin.weight for lin in self.__edge_message_transformation_layers]
+        for i, w in enumerate(weights):
+            _check_shape(w, (self.__message_dimension, H + Fd), f"edge weight {i}")
+        feats = C._edge_feature_list(edge_features, plan, Fd, h.device)
+        msg = C.first_layer_messages(plan, gsrc, None, weights, [None] * plan.num_types, feats, H)
+        agg = C.segment_reduce(msg, plan, reduce)
+        return C.grucell(agg, h, self.__state_update)
 
     # ---- derived-weight cache ------------------------------------------------------------------------------------------
     def _weight_cache(self, kind: str, nbytes: int, params: List[torch.Tensor], device: torch.device):
@@ -358,8 +379,30 @@ class MLP(nn.Module):
     def single_linear(self) -> nn.Linear:
         return self.__mlp_modules[1]
 
+    @property
+    def linears(self) -> List[nn.Linear]:
+        return [m for m in self.__mlp_modules if isinstance(m, nn.Linear)]
+
+    @property
+    def activation(self) -> Optional[nn.Module]:
+        acts = [m for m in self.__mlp_modules if not isinstance(m, (nn.Linear, nn.Dropout))]
+        return acts[0] if acts else None
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError("MLP is executed inside the fused edge-message kernel, not as a stand-alone module")
+        """mlp.py:79-80 on the native dense kernel (one launch per Linear, bias + activation fused); eval-mode dropout = identity.
+        Inside MlpMessagePassingLayer the zero-hidden-layer form never runs as a module: it is the fused kernel's per-type weight."""
+        from . import composed as C
+
+        if self.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.__mlp_modules):
+            raise NotImplementedError("training-mode dropout has no native kernel (forward-only)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("ptgnn_b200.MLP is forward-only: call it under torch.no_grad()")
+        lead = x.shape[:-1]
+        y = x.reshape(-1, x.shape[-1]).to(torch.float32)
+        lin = self.linears
+        for i, layer in enumerate(lin):
+            y = C.linear(y, layer.weight, layer.bias, self.activation if i + 1 < len(lin) else None)
+        return y.reshape(*lead, y.shape[-1]).to(x.dtype)
 
 
 class MlpMessagePassingLayer(AbstractMessagePassingLayer):
@@ -424,14 +467,11 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
     ) -> torch.Tensor:
         mlps = self.__edge_message_transformation_layers
         assert len(adjacency_lists) == len(mlps), "The number of adjacency lists must be equal to the number of edge types."
-        if not isinstance(self.__aggregation_fn, str):
-            raise NotImplementedError("module aggregators (e.g. PnaMessageAggregation) have no native kernel yet (SURVEY.md §8 f-3)")
-        if any(m.num_hidden_layers != 0 or m.uses_biases for m in mlps):
-            raise NotImplementedError("message MLPs with hidden layers / biases have no native kernel yet")
-        if self.__features_dim != 0:
-            raise NotImplementedError("edge features (F > 0) have no native kernel yet (SURVEY.md §8 row f-4)")
-        _check_no_edge_features(edge_features)
         _refuse_autograd(self, node_states)
+        if (not isinstance(self.__aggregation_fn, str) or self.__features_dim != 0
+                or any(m.num_hidden_layers != 0 or m.uses_biases for m in mlps)):
+            return self._forward_composed(node_states, adjacency_lists, edge_features, gather_states)
+        _check_no_edge_features(edge_features)
         reduce = _reduce_code(self.__aggregation_fn)
         msg_act = _activation_code(self.__message_activation, "message_activation")
 
@@ -513,6 +553,46 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
             )
         N.check(rc, "ptgnn_b200_mlp_forward_f32")
         return out
+
+    def _forward_composed(self, node_states, adjacency_lists, edge_features, gather_states) -> torch.Tensor:
+        """Module aggregators (PNA ...), message MLPs with hidden layers / biases, edge features (mlpmessagepassing.py:82-117 in
+        full generality): stand-alone native pieces + the module's own tail -- see ptgnn_b200/composed.py.  fp32 states only."""
+        from . import composed as C
+
+        if node_states.dtype != torch.float32:
+            raise NotImplementedError("this MlpMessagePassingLayer configuration has no bf16 kernel")
+        _check_states(node_states, self.__input_state_dim, "MlpMessagePassingLayer")
+        for m in self.__state_update:
+            if isinstance(m, nn.Dropout) and self.training and m.p > 0:
+                raise NotImplementedError("training-mode dropout has no native kernel (forward-only)")
+        h = N.require_cuda(node_states, "node_states", torch.float32)
+        gsrc = h if gather_states is None else N.require_cuda(gather_states, "gather_states", torch.float32)
+        plan = self._plan(adjacency_lists, h.shape[0], None if gather_states is None else gsrc.shape[0])
+        mlps = list(self.__edge_message_transformation_layers)
+        ut = self.__use_target_state_as_message_input
+        state_cols = (2 if ut else 1) * self.__input_state_dim
+        feats = C._edge_feature_list(edge_features, plan, self.__features_dim, h.device)
+        firsts = [m.linears[0] for m in mlps]
+        for i, lin in enumerate(firsts):
+            _check_shape(lin.weight, (lin.out_features, state_cols + self.__features_dim), f"message MLP {i} first layer")
+        msg = C.first_layer_messages(plan, gsrc, h if ut else None, [l.weight for l in firsts], [l.bias for l in firsts], feats, state_cols)
+        depth = len(mlps[0].linears)
+        for k in range(1, depth):                       # hidden layers: activation, then one dense GEMM per edge type
+            act = mlps[0].activation
+            msg = act(msg) if act is not None else msg
+            nxt = torch.empty(plan.num_edges, mlps[0].linears[k].out_features, dtype=torch.float32, device=h.device)
+            for t, m in enumerate(mlps):
+                lo, hi = plan.type_off[t], plan.type_off[t + 1]
+                if hi > lo:
+                    nxt[lo:hi] = C.linear(msg[lo:hi], m.linears[k].weight, m.linears[k].bias)
+            msg = nxt
+        if isinstance(self.__aggregation_fn, str):
+            agg = C.segment_reduce(msg, plan, _reduce_code(self.__aggregation_fn))
+        else:   # e.g. the reference's PnaMessageAggregation: messages + concatenated targets, as mlpmessagepassing.py:100-112 passes them
+            agg = self.__aggregation_fn(msg, plan.tgt32.to(torch.int64), h.shape[0])
+        if self.__message_activation is not None:
+            agg = self.__message_activation(agg)
+        return self.__state_update(agg)
 
     @property
     def input_state_dimension(self) -> int:

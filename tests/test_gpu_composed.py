@@ -1,0 +1,145 @@
+"""The composed path (ptgnn_b200/composed.py): edge features, message MLPs with hidden layers and the
+stand-alone ``MLP.forward`` (a7), module aggregators such as PNA (f-3) and the other torch_scatter consumers behind the shim
+(GraphNorm / log-softmax heads), against torch-CPU restatements of the reference formulas (oracle functions where they exist)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import assert_close, gated_oracle_args, random_adjacency
+from oracle import ptgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(adj):
+    return [(s.cuda(), t.cuda()) for s, t in adj]
+
+
+def test_mlp_module_forward():
+    """mlp.py:79-80: Dropout/Linear/activation chain, no final activation, optional biases."""
+    import ptgnn_b200 as P
+
+    torch.manual_seed(0)
+    for kw in (dict(hidden_layers=[48, 20], use_biases=True), dict(hidden_layers=1), dict(hidden_layers=0), dict(hidden_layers=[7], use_biases=True,
+                                                                                                               activation=torch.nn.Tanh())):
+        mlp = P.MLP(36, 24, **kw).eval()
+        x = torch.randn(500, 36)
+        ref = x
+        lins = mlp.linears
+        for i, l in enumerate(lins):
+            ref = F.linear(ref, l.weight, l.bias)
+            if i + 1 < len(lins):
+                ref = mlp.activation(ref)
+        with torch.no_grad():
+            got = mlp.cuda()(x.cuda())
+        assert_close(got, ref.detach(), what=f"MLP {kw}")
+
+
+@pytest.mark.parametrize("agg", ["sum", "max"])
+@pytest.mark.parametrize("F_dim", [8, 6])
+def test_gated_layer_with_edge_features(agg, F_dim):
+    import ptgnn_b200 as P
+
+    gen = torch.Generator().manual_seed(F_dim)
+    torch.manual_seed(1)
+    n, H, counts = 700, 64, [2000, 0, 900]
+    adj = random_adjacency(gen, n, counts)
+    feats = [torch.randn(c, F_dim, generator=gen) for c in counts]
+    h = torch.randn(n, H, generator=gen)
+    layer = P.GatedMessagePassingLayer(H, H, len(counts), agg, edge_feature_dimension=F_dim).cuda().eval()
+    ref = O.gated_layer_forward(h, adj, feats, aggregation_fn=agg, **gated_oracle_args({k: v.cpu() for k, v in layer.state_dict().items()}))
+    with torch.no_grad():
+        got = layer(h.cuda(), _dev(adj), edge_features=[f.cuda() for f in feats])
+    assert_close(got, ref, what=f"gated with F={F_dim} {agg}")
+
+
+@pytest.mark.parametrize("hidden,F_dim,use_target", [(1, 0, True), ([40], 8, True), (0, 12, False)])
+def test_mlp_layer_hidden_layers_and_edge_features(hidden, F_dim, use_target):
+    import ptgnn_b200 as P
+
+    gen = torch.Generator().manual_seed(5)
+    torch.manual_seed(2)
+    n, H, D, counts = 600, 64, 64, [1800, 700]
+    adj = random_adjacency(gen, n, counts)
+    feats = [torch.randn(c, F_dim, generator=gen) for c in counts]
+    h = torch.randn(n, H, generator=gen)
+    layer = P.MlpMessagePassingLayer(H, H, D, len(counts), "max", mlp_hidden_layers=hidden, features_dimension=F_dim,
+                                     use_target_state_as_message_input=use_target).cuda().eval()
+    sd = {k: v.cpu() for k, v in layer.state_dict().items()}
+    p = "_MlpMessagePassingLayer__"
+    n_lin = len(layer._MlpMessagePassingLayer__edge_message_transformation_layers[0].linears)
+    ws = [[sd[f"{p}edge_message_transformation_layers.{t}._MLP__mlp_modules.{1 + 3 * k if k else 1}.weight"] for k in range(n_lin)]
+          for t in range(len(counts))]
+    ref = O.mlp_layer_forward(h, adj, feats, ws, "max", use_target_state_as_message_input=use_target,
+                              ln_weight=sd[p + "state_update.0.weight"], ln_bias=sd[p + "state_update.0.bias"],
+                              dense_weight=sd[p + "state_update.1.weight"], dense_bias=sd[p + "state_update.1.bias"])
+    with torch.no_grad():
+        got = layer(h.cuda(), _dev(adj), edge_features=[f.cuda() for f in feats])
+    assert_close(got, ref, tol=2e-5, what=f"mlp hidden={hidden} F={F_dim}")     # LayerNorm amplifies upstream rounding
+
+
+def _pna_reference(messages, targets, n, delta=1.0):
+    """pna_aggregation.py:27-56 on CPU with torch scatter_reduce."""
+    deg = torch.zeros(n).index_add_(0, targets, torch.ones(targets.shape[0]))
+    s = torch.zeros(n, messages.shape[1]).index_add_(0, targets, messages)
+    mean = s / (deg.unsqueeze(-1) + 1e-5)
+    idx = targets.unsqueeze(-1).expand_as(messages)
+    mx = torch.zeros(n, messages.shape[1]).scatter_reduce(0, idx, messages, "amax", include_self=False)
+    mn = torch.zeros(n, messages.shape[1]).scatter_reduce(0, idx, messages, "amin", include_self=False)
+    comp = torch.relu(messages.pow(2) - mean[targets].pow(2)) + 1e-10
+    std = torch.sqrt(torch.zeros(n, messages.shape[1]).index_add_(0, targets, comp))
+    allagg = torch.cat([s, mean, mx, mn, std], -1)
+    p1 = torch.log(deg + 1).unsqueeze(-1) / delta
+    return torch.cat([allagg, allagg * p1, allagg / (p1 + 1e-3) * 1.0], -1) if False else torch.cat([allagg, allagg * p1, allagg * (1 / (p1 + 1e-3))], -1)
+
+
+def test_mlp_layer_with_pna_aggregator():
+    import ptgnn_b200 as P
+
+    gen = torch.Generator().manual_seed(7)
+    torch.manual_seed(3)
+    n, H, D, counts = 500, 64, 32, [1500, 600]
+    adj = random_adjacency(gen, n, counts)
+    h = torch.randn(n, H, generator=gen)
+    layer = P.MlpMessagePassingLayer(H, 48, D, len(counts), P.PnaMessageAggregation(delta=2.0)).cuda().eval()
+    sd = {k: v.cpu() for k, v in layer.state_dict().items()}
+    p = "_MlpMessagePassingLayer__"
+    msgs = []
+    for t, (s, tg) in enumerate(adj):
+        w = sd[f"{p}edge_message_transformation_layers.{t}._MLP__mlp_modules.1.weight"]
+        msgs.append(F.linear(torch.cat([h[s], h[tg]], -1), w))
+    agg = _pna_reference(torch.cat(msgs), torch.cat([a[1] for a in adj]), n, delta=2.0)
+    ref = torch.tanh(F.linear(F.layer_norm(F.gelu(agg), (agg.shape[1],), sd[p + "state_update.0.weight"], sd[p + "state_update.0.bias"]),
+                              sd[p + "state_update.1.weight"], sd[p + "state_update.1.bias"]))
+    with torch.no_grad():
+        got = layer(h.cuda(), _dev(adj))
+    assert got.shape == (n, 48)
+    assert_close(got, ref, tol=3e-5, what="mlp + PNA")
+
+
+def test_torch_scatter_shim_composites_and_graphnorm_shape():
+    """scatter_log_softmax / logsumexp (varmisuse.py:79-88, varsizedsummary.py:57), scatter_mean over node_to_graph_idx
+    (graphnorm.py:36-41), 1-D inputs, non-multiple-of-4 widths, arg of scatter_max."""
+    from ptgnn_b200 import torch_scatter_shim as ts
+
+    gen = torch.Generator().manual_seed(9)
+    idx = torch.sort(torch.randint(0, 40, (3000,), generator=gen)).values
+    x1 = torch.randn(3000, generator=gen)
+    x2 = torch.randn(3000, 7, generator=gen)
+    # reference formulas on the CPU
+    def seg_lse(x, i, n):
+        mx = torch.full((n,) + x.shape[1:], -float("inf")).scatter_reduce(0, i.view(-1, *[1] * (x.dim() - 1)).expand_as(x), x, "amax")
+        mx = torch.where(torch.isinf(mx), torch.zeros_like(mx), mx)
+        s = torch.zeros((n,) + x.shape[1:]).index_add_(0, i, (x - mx[i]).exp())
+        return (s + 1e-12).log() + mx
+    got = ts.scatter_log_softmax(x1.cuda(), idx.cuda(), dim=0, eps=0).cpu()
+    ref = x1 - seg_lse(x1, idx, 40)[idx]
+    assert_close(got, ref, tol=2e-5, what="scatter_log_softmax 1-D")
+    got = ts.scatter_logsumexp(x2.cuda(), idx.cuda(), dim=0, dim_size=40).cpu()
+    assert_close(got, seg_lse(x2, idx, 40), tol=2e-5, what="scatter_logsumexp [E, 7]")
+    mean = ts.scatter_mean(x2.cuda(), idx.cuda(), dim=0).cpu()
+    cnt = torch.bincount(idx, minlength=40).clamp(min=1).unsqueeze(-1)
+    assert_close(mean, torch.zeros(40, 7).index_add_(0, idx, x2) / cnt, what="scatter_mean")
+    out, arg = ts.scatter_max(x1.cuda(), idx.cuda())
+    ref_max = torch.full((40,), -float("inf")).scatter_reduce(0, idx, x1, "amax")
+    assert torch.equal(out.cpu(), ref_max) and torch.equal(x1[arg.cpu()], ref_max)

@@ -83,10 +83,14 @@ def test_unsupported_configurations_fail_loudly():
     with torch.no_grad():
         with pytest.raises(NotImplementedError):  # training-mode dropout
             P.GatedMessagePassingLayer(32, 32, 1, "sum", dropout_rate=0.5).train()(torch.zeros(4, 32), adj)
-        with pytest.raises(NotImplementedError):  # hidden MLP layers
+        with pytest.raises(N.NativeLibraryError):  # hidden MLP layers are supported (composed path) -- on CUDA tensors only
             P.MlpMessagePassingLayer(32, 32, 32, 1, "sum", mlp_hidden_layers=1).eval()(torch.zeros(4, 32), adj)
         with pytest.raises(NotImplementedError):  # unknown aggregation
             P.GatedMessagePassingLayer(32, 32, 1, "median").eval()(torch.zeros(4, 32), adj)
+        with pytest.raises(ValueError):  # width mismatch is a shape error, not a read past the weight buffers
+            P.GatedMessagePassingLayer(32, 32, 1, "sum").eval()(torch.zeros(4, 64), adj)
+        with pytest.raises(ValueError):
+            P.MlpMessagePassingLayer(32, 32, 32, 1, "sum").eval()(torch.zeros(4, 32, 1), adj)
 
 
 def test_container_metrics_protocol():
