@@ -18,24 +18,25 @@ using tc::mbar_init;
 using tc::mbar_wait;
 
 // ---- geometry ------------------------------------------------------------------------------------------------------
-constexpr int NUM_THREADS = 12 * 32;
+constexpr int NUM_THREADS = 16 * 32;
 constexpr int MMA_WARP = 4;
 constexpr int GATHER_WARP0 = 5, GATHER_THREADS = 64;
 constexpr int SCHED_WARP = 7;
-constexpr int EPI_WARP0 = 8, EPI_THREADS = 128;
-constexpr int NUM_CONSUMER_WARPS = 4 + 1 + 2 + 4;      // weight loaders, MMA, gatherers, epilogue (scheduler table readers)
+constexpr int EPI_THREADS = 256;                       // two epilogue warpgroups (warps 0-3, 8-11): lower / upper half of a block's targets
+constexpr int NUM_CONSUMER_WARPS = 4 + 1 + 2 + 8;      // weight loaders, MMA, gatherers, epilogue (scheduler table readers)
 constexpr int NUM_SLOTS = 3, LOOKAHEAD = 2;
 constexpr int SLOT_BYTES = 32768;
 constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
 constexpr int META_RING = 8;
 constexpr int SCHED_RING = 4;
-constexpr int MID_REGS = 80, EPI_REGS = 200;      // weight loaders keep the launch bound (168): (168 + 80 + 200) * 128 = 57344 <= 65536
+constexpr int W_REGS = 184, MID_REGS = 72;        // 512 threads launch with 128 registers each; warps 4-7 give 56 back, the weight loaders take them: (184 + 72 + 128 + 128) * 128 = 65536
 constexpr int ACC_TMEM_OFF = 256;                               // weight buffers below, accumulators above
 constexpr int EPI_BAR_ID = 2;
 
 struct Meta {                     // per sub-group: what the epilogue needs to know about the accumulator columns
     int32_t tloff[128];           // byte offset of the column's target row inside agg_s (0 for columns >= n)
     uint32_t endmask[4];          // bit c: column c is the last edge of its (target, type) segment
+    uint32_t lowmask[4];          // bit c: column c's target lies in the lower half of the block (epilogue warpgroup 0's columns)
     int32_t n, pad[3];
 };
 struct Sched {                    // one target block: its id and the T+1 sorted-edge offsets of its (block, type) groups
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
         for (int s = 0; s < NUM_SLOTS; ++s) { mbar_init(&x_full[s], GATHER_THREADS); mbar_init(&x_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&w_full[b], 128); mbar_init(&w_empty[b], 1);
-            mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4);
+            mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8);
         }
         for (int r = 0; r < SCHED_RING; ++r) { mbar_init(&sched_full[r], 1); mbar_init(&sched_empty[r], NUM_CONSUMER_WARPS); }
         tc::mbar_init_fence();
@@ -217,47 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_smem, 0);
     const int T = p.T;
 
-    if (warp < 4) {
-        // ============================================ WEIGHT LOADERS ============================================
-        // Thread d owns TMEM lane d = row d of W_t.  The packed weights are laid out so that a warp-wide 16-byte load is one
-        // contiguous 512-byte burst: wpack[(((t * NSEG + seg) * NPART + part) * (K / 8) + c4) * 128 + d] = columns 4 c4 .. 4 c4 + 3.
-        // All loads of a (type, segment) are in flight before the buffer's release is awaited.
-        const int d = warp * 32 + lane;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
-        uint32_t wl = 0;
-        Step s;
-        for (;;) {
-            const int ev = gen.next(s);
-            if (ev == 2) break;
-            if (ev == 1 || !s.first_sub) continue;
-            const uint4 *src = p.wpack + ((size_t)(s.t * NSEG + s.seg) * NPART * (K / 8)) * 128 + d;
-            uint32_t w[NPART][K / 2];
-#pragma unroll
-            for (int part = 0; part < NPART; ++part)
-#pragma unroll
-                for (int c4 = 0; c4 < K / 8; ++c4) {
-                    const uint4 v = ldg_nc_u4(src + (size_t)(part * (K / 8) + c4) * 128);
-                    w[part][4 * c4] = v.x; w[part][4 * c4 + 1] = v.y; w[part][4 * c4 + 2] = v.z; w[part][4 * c4 + 3] = v.w;
-                }
-            const uint32_t wb = wl & 1;
-            mbar_wait(&w_empty[wb], ((wl >> 1) & 1) ^ 1);        // the MMAs that read this buffer two loads ago are done
-            tc::tc_fence_after_sync();
-#pragma unroll
-            for (int part = 0; part < NPART; ++part)
-#pragma unroll
-                for (int j = 0; j < WPART_COLS / 32; ++j) {
-                    uint32_t chunk[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) chunk[i] = w[part][32 * j + i];
-                    tmem_st_32cols_u32(tmem_lane + wb * WBUF_COLS + part * WPART_COLS + 32 * j, chunk);
-                }
-            tc::tmem_st_wait();
-            tc::tc_fence_before_sync();
-            mbar_arrive(&w_full[wb]);
-            ++wl;
-        }
-    } else if (warp < 8) {
+    if (warp >= 4 && warp < 8) {
         tc::reg_dealloc<MID_REGS>();
         if (warp == MMA_WARP) {
             // ============================================ MMA ISSUER ============================================
@@ -377,7 +338,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     const bool end = valid && tl_b[half] != tl_a[half];      // last column (tl_b = -2) or the target changes
                     m->tloff[c] = valid ? tl_a[half] * (kD * 4) : 0;
                     const uint32_t word = __ballot_sync(0xffffffffu, end);
-                    if (lane == 0) m->endmask[c >> 5] = word;
+                    const uint32_t low = __ballot_sync(0xffffffffu, valid && tl_a[half] < (p.B >> 1));
+                    if (lane == 0) { m->endmask[c >> 5] = word; m->lowmask[c >> 5] = low; }
                 }
                 if (g == 0) m->n = st.n;
                 ++sgc;
@@ -421,20 +383,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             }
             cp_async_wait<0>();
         }
-    } else {
+    } else if (warp < 12) {
         // ============================================ EPILOGUE ============================================
         // Thread d owns message feature d = TMEM lane d and column d of agg_s.  For every accumulator column (edge) in plan
         // order: value = main (+ 2^-11 correction); at the first edge of a (target, type) segment the running value is
         // (re)loaded from agg_s[target][d], at the last one it is stored back -- a target's messages are accumulated one by one
-        // in the reference's order, across types and sub-groups.  All agg_s reads of a 32-column batch are issued up front.
-        tc::reg_alloc<EPI_REGS>();
-        const int ew = warp - EPI_WARP0;
+        // in the reference's order, across types and sub-groups.
+        // TWO warpgroups (a single warp per scheduler is latency-bound: measured IPC 0.17): group 0 takes the columns whose
+        // target lies in the lower half of the block, group 1 the upper half.  Edges are sorted by target, so each group owns a
+        // contiguous column range of every sub-group (split = number of lower-half columns) and the two never touch the same
+        // agg_s row -- no synchronisation between them except at the block's write-out.
+        const int eg = warp >> 3, ew = warp & 3;             // warps 0-3: group 0, warps 8-11: group 1
         const int d = ew * 32 + lane;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC_TMEM_OFF;
         const uint32_t aggcol_s = smem_u32(agg_s + d);      // shared-space address of agg_s[0][d]
         const float IDENT = red_identity<RED>();
         StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
-        for (int r = 0; r < p.B; ++r) agg_s[r * kD + d] = IDENT;
+        const int row_lo = eg == 0 ? 0 : (p.B >> 1), row_hi = eg == 0 ? (p.B >> 1) : p.B;     // rows this group initialises
+        for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
         uint32_t sg = 0;
         float acc = IDENT;
         Step s;
@@ -448,18 +414,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 tc::tc_fence_after_sync();
                 const Meta *m = &meta_ring[sg % META_RING];
                 const int n = s.n;
-                uint32_t carry = 1u;                       // the first column of a sub-group always (re)loads its target's value
-                // W = 32 or 16 accumulator columns per batch (tails of <= 16 columns take the narrow form)
-                auto batch = [&](auto width_tag, int c0) {
-                    constexpr int W = decltype(width_tag)::value;
+                int split = __popc(m->lowmask[0]) + __popc(m->lowmask[1]);
+                if (NMAX > 64) split += __popc(m->lowmask[2]) + __popc(m->lowmask[3]);
+                const int c_lo = eg == 0 ? 0 : split, c_hi = eg == 0 ? split : n;       // this group's columns
+                for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
+                    constexpr int W = 16;
                     uint32_t vm[W], vc[W];
-                    if (W == 32) {
-                        tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + c0, reinterpret_cast<uint32_t (&)[32]>(vm));
-                        if (NPROD == 3) tc::tmem_ld_32cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, reinterpret_cast<uint32_t (&)[32]>(vc));
-                    } else {
-                        tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, reinterpret_cast<uint32_t (&)[16]>(vm));
-                        if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, reinterpret_cast<uint32_t (&)[16]>(vc));
-                    }
+                    tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
+                    if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
                     uint32_t addr[W];
 #pragma unroll
                     for (int j = 0; j < W / 4; ++j) {
@@ -467,17 +429,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                         addr[4 * j] = aggcol_s + o.x; addr[4 * j + 1] = aggcol_s + o.y;
                         addr[4 * j + 2] = aggcol_s + o.z; addr[4 * j + 3] = aggcol_s + o.w;
                     }
-                    uint32_t endw = m->endmask[c0 >> 5] >> (c0 & 31);
-                    if (W == 16) endw &= 0xFFFFu;
-                    const uint32_t startw = (endw << 1) | carry;
-                    carry = (endw >> (W - 1)) & 1u;
+                    const uint32_t endw = (m->endmask[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+                    // the column before this batch ended a segment (or the batch opens the sub-group: always reload)
+                    const uint32_t prev_end = c0 == 0 ? 1u : (m->endmask[(c0 - 1) >> 5] >> ((c0 - 1) & 31)) & 1u;
+                    const uint32_t startw = (endw << 1) | prev_end;
+                    // columns of the batch that belong to this group: [max(c_lo, c0), min(c_hi, c0 + 16))
+                    const int first = c_lo > c0 ? c_lo - c0 : 0, last = c_hi - c0 < W ? c_hi - c0 : W;
+                    const uint32_t storew = endw & (0xFFFFu << first) & (0xFFFFu >> (W - last));
                     float pre[W];
 #pragma unroll
                     for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
                     tc::tmem_ld_wait();
                     // t[c] = op(pre[c], v[c]) for every column (independent); a column that CONTINUES a segment (rare: most
                     // (target, type) segments hold one edge) then overwrites it with op(t[c-1], v[c]) -- a predicated op, in
-                    // column order, so a target's messages are still combined one by one in plan order
+                    // column order, so a target's messages are still combined one by one in plan order.  Columns of the other
+                    // group are computed but never stored; this group's first column always starts a segment.
                     float t[W];
 #pragma unroll
                     for (int c = 0; c < W; ++c) {
@@ -492,11 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     for (int c = 1; c < W; ++c) continue_segment<RED>(t[c], t[c - 1], __uint_as_float(vm[c]), startw & (1u << c));
                     acc = t[W - 1];
 #pragma unroll
-                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], t[c], endw & (1u << c));
-                };
-                for (int c0 = 0; c0 < n; c0 += 32) {
-                    if (n - c0 <= 16) batch(std::integral_constant<int, 16>{}, c0);
-                    else batch(std::integral_constant<int, 32>{}, c0);
+                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], t[c], storew & (1u << c));
                 }
                 tc::tc_fence_before_sync();
                 __syncwarp();
@@ -504,11 +466,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 ++sg;
                 continue;
             }
-            // ---- block finished: every column of agg_s is final once all four warps are here ----
+            // ---- block finished: every column of agg_s is final once all eight warps are here ----
             named_bar_sync(EPI_BAR_ID, EPI_THREADS);
             const int row0 = s.blk * p.B;
             const int rows = min(p.B, p.num_nodes - row0);
-            for (int r = ew; r < rows; r += 4) {
+            for (int r = eg * 4 + ew; r < rows; r += 8) {
                 float4 a = *reinterpret_cast<const float4 *>(agg_s + r * kD + lane * 4);
                 const int v = row0 + r;
                 if (RED == PTGNN_REDUCE_MEAN) {
@@ -558,7 +520,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 }
             }
             named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-            for (int r = 0; r < p.B; ++r) agg_s[r * kD + d] = IDENT;
+            for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
+        }
+    } else {
+        // ============================================ WEIGHT LOADERS ============================================
+        // Thread d owns TMEM lane d = row d of W_t.  The packed weights are laid out so that a warp-wide 16-byte load is one
+        // contiguous 512-byte burst: wpack[(((t * NSEG + seg) * NPART + part) * (K / 8) + c4) * 128 + d] = columns 4 c4 .. 4 c4 + 3.
+        // All loads of a (type, segment) are in flight before the buffer's release is awaited.
+        tc::reg_alloc<W_REGS>();                   // granted once warps 4-7 have released theirs
+        const int d = (warp & 3) * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
+        uint32_t wl = 0;
+        Step s;
+        for (;;) {
+            const int ev = gen.next(s);
+            if (ev == 2) break;
+            if (ev == 1 || !s.first_sub) continue;
+            // 64 TMEM columns (16 16-byte loads, 64 registers) per round: 512 threads leave 128 registers per thread, so the 128
+            // columns of an fp32 (hi | lo') weight buffer go in two rounds; the first round's loads are issued before the
+            // buffer's release is awaited (the loaders run up to two groups ahead of the MMAs)
+            constexpr int ROUND = WBUF_COLS, NROUNDS = 1;          // all of a buffer's loads in flight at once (W_REGS registers)
+            const uint4 *src = p.wpack + ((size_t)(s.t * NSEG + s.seg) * NPART * (K / 8)) * 128 + d;
+            uint32_t w[ROUND];
+            auto load_round = [&](int r) {
+#pragma unroll
+                for (int j = 0; j < ROUND / 4; ++j) {
+                    const uint4 v = ldg_nc_u4(src + (size_t)(r * (ROUND / 4) + j) * 128);
+                    w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+                }
+            };
+            load_round(0);
+            const uint32_t wb = wl & 1;
+            mbar_wait(&w_empty[wb], ((wl >> 1) & 1) ^ 1);        // the MMAs that read this buffer two loads ago are done
+            tc::tc_fence_after_sync();
+#pragma unroll
+            for (int r = 0; r < NROUNDS; ++r) {
+#pragma unroll
+                for (int j = 0; j < ROUND / 32; ++j) {
+                    uint32_t chunk[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) chunk[i] = w[32 * j + i];
+                    tmem_st_32cols_u32(tmem_lane + wb * WBUF_COLS + r * ROUND + 32 * j, chunk);
+                }
+                if (r + 1 < NROUNDS) {
+                    tc::tmem_st_wait();                            // the stores have read their registers
+                    load_round(r + 1);
+                }
+            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before_sync();
+            mbar_arrive(&w_full[wb]);
+            ++wl;
         }
     }
     tc::tc_fence_before_sync();

@@ -27,9 +27,12 @@
 // represented: the packing kernels raise a status flag and the host raises (PTGNN_B200_FP32_MODE=tf32 selects the
 // unfused 3xTF32 kernels).
 //
-// Roles (12 warps):  0-3 WEIGHT LOADERS (global -> registers -> tcgen05.st, TMEM A buffers, double buffered) |
+// Roles (16 warps):  0-3 and 8-11 EPILOGUE, two warpgroups: thread d <-> TMEM lane d; group 0 takes the columns whose target
+//   lies in the lower half of the block, group 1 the upper half (disjoint agg_s rows, no synchronisation between them) |
 //   4 MMA issuer | 5-6 ROW GATHERERS (16-byte cp.async into a 3-slot ring, SWIZZLE_128B K-major) |
-//   7 SCHEDULER (block -> group offsets table ring) | 8-11 EPILOGUE (thread d <-> TMEM lane d).
+//   7 SCHEDULER (block -> group offsets table ring) |
+//   12-15 WEIGHT LOADERS (global -> registers -> tcgen05.st, TMEM A buffers, double buffered; setmaxnreg gives them the
+//   registers warps 4-7 release -- ptxas only extends a role's budget when that role is the LAST branch of the kernel).
 // TMEM (512 columns): [0,256) two weight buffers | [256,512) two accumulator sets (main | correction).
 #pragma once
 #include "common.cuh"
