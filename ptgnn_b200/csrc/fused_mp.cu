@@ -58,6 +58,7 @@ struct Params {
     void *out;
     int num_nodes, num_blocks, B, T, reduce, out_mode;
     int32_t *status;
+    unsigned long long *trace;     // debug (PTGNN_FUSED_TRACE=1): per-role event timeline of CTA 0, else nullptr
     Epilogue epi;
 };
 
@@ -86,6 +87,19 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p) {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ uint32_t swz(int row, int q) { return (uint32_t)(row * 128 + ((q ^ (row & 7)) << 4)); }
+
+// Debug timeline (PTGNN_FUSED_TRACE=1): CTA 0, one thread per role, records (clock64, step, tag) at the pipeline hand-offs into its
+// 2048-entry region of the trace buffer; read back with ptgnn_b200_debug_fused_trace (tools/fused_trace.py).
+struct Trace {
+    unsigned long long *buf;
+    int n;
+    __device__ __forceinline__ void mark(int tag, uint32_t step) {
+        if (buf != nullptr && n < 2048) buf[n++] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(step & 0xFFFFu) << 8) | (unsigned)(tag & 0xFF);
+    }
+};
+__device__ __forceinline__ Trace make_trace(unsigned long long *base, int role, bool on) {
+    return Trace{(base != nullptr && blockIdx.x == 0 && on) ? base + role * 2048 : nullptr, 0};
+}
 
 // ---- the (block, group, sub-group, segment) walk every role performs in the same order -----------------------------------
 struct Step { int blk, t, e, n, seg; bool first_sub, last_sub; };
@@ -225,6 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             const bool leader = tc::elect_one();
             StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
             uint32_t xs = 0, sg = 0, wl = 0, wl0 = 0;
+            Trace tr = make_trace(p.trace, 1, leader);
             Step s;
             for (;;) {
                 const int ev = gen.next(s);
@@ -232,13 +247,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 if (ev == 1) continue;
                 if (s.first_sub && s.seg == 0) { wl0 = wl; wl += NSEG; }
                 const uint32_t ab = sg & 1;
+                tr.mark(10, xs);
                 if (s.seg == 0) {
                     mbar_wait(&acc_empty[ab], ((sg >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator set
                 }
+                tr.mark(11, xs);
                 const uint32_t slot = xs % NUM_SLOTS;
                 mbar_wait(&x_full[slot], (xs / NUM_SLOTS) & 1);
                 const uint32_t wli = wl0 + s.seg, wb = wli & 1;
+                tr.mark(12, xs);
                 if (s.first_sub) mbar_wait(&w_full[wb], (wli >> 1) & 1);
+                tr.mark(13, xs);
                 tc::tc_fence_after_sync();
                 const uint32_t n16 = (uint32_t)(s.n + 15) & ~15u;
                 const uint32_t idesc = tc::make_instr_desc(FMT, 128, n16);
@@ -266,6 +285,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 if (leader && s.last_sub) tc::mma_commit(&w_empty[wb]);
                 if (leader && s.seg == NSEG - 1) tc::mma_commit(&acc_full[ab]);
                 __syncwarp();
+                tr.mark(14, xs);
                 ++xs;
                 if (s.seg == NSEG - 1) ++sg;
             }
@@ -296,6 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             const int q = g & 7, rsub = g >> 3;
             StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
             uint32_t c_issue = 0, c_done = 0, sgc = 0;
+            Trace tr = make_trace(p.trace, 0, g == 0);
             // Everything a step needs from global memory (row indices, the targets of its columns) is loaded ONE STEP AHEAD:
             // `fetch` only issues the loads, the copies of the current step are issued while they are in flight, `finish_meta`
             // consumes them afterwards.
@@ -352,7 +373,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 finish_meta(cur);                      // consumes the loads of the PREVIOUS call
                 fetch();                               // loads for the following step: in flight during the copies below
                 const uint32_t slot = c_issue % NUM_SLOTS;
+                tr.mark(1, c_issue);
                 mbar_wait(&x_empty[slot], ((c_issue / NUM_SLOTS) & 1) ^ 1);
+                tr.mark(2, c_issue);
                 const unsigned char *rows = cur.seg == 0 ? p.src_rows : p.tgt_rows;
                 const uint32_t sbase = smem_u32(ring + slot * SLOT_BYTES) + swz(rsub, q);
 #pragma unroll
@@ -364,6 +387,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                             cp_async16(sbase + ti * TILE_BYTES + i * 1024, src + (ti / KCH) * (K * 2) + (ti % KCH) * 128, 16);
                     }
                 }
+                tr.mark(3, c_issue);
                 ++c_issue;
             };
             fetch();
@@ -376,6 +400,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             while (c_done < c_issue) {
                 cp_async_wait<LOOKAHEAD - 1>();          // this thread's pieces of step c_done have landed ...
                 tc::fence_proxy_async_smem();            // ... and are visible to the tensor core (async proxy)
+                tr.mark(4, c_done);
                 mbar_arrive(&x_full[c_done % NUM_SLOTS]);
                 ++c_done;
                 if (more) { issue_next(); more = has_nxt; }
@@ -403,6 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
         for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
         uint32_t sg = 0;
         float acc = IDENT;
+        Trace tr = make_trace(p.trace, 2 + eg, ew == 0 && lane == 0);
         Step s;
         for (;;) {
             const int ev = gen.next(s);
@@ -410,7 +436,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             if (ev == 0) {
                 if (s.seg != NSEG - 1) continue;
                 const uint32_t ab = sg & 1;
+                tr.mark(20, sg);
                 mbar_wait(&acc_full[ab], (sg >> 1) & 1);
+                tr.mark(21, sg);
                 tc::tc_fence_after_sync();
                 const Meta *m = &meta_ring[sg % META_RING];
                 const int n = s.n;
@@ -463,10 +491,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 tc::tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                tr.mark(22, sg);
                 ++sg;
                 continue;
             }
             // ---- block finished: every column of agg_s is final once all eight warps are here ----
+            tr.mark(23, sg);
             named_bar_sync(EPI_BAR_ID, EPI_THREADS);
             const int row0 = s.blk * p.B;
             const int rows = min(p.B, p.num_nodes - row0);
@@ -521,6 +551,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             }
             named_bar_sync(EPI_BAR_ID, EPI_THREADS);
             for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
+            tr.mark(24, sg);
         }
     } else {
         // ============================================ WEIGHT LOADERS ============================================
@@ -532,11 +563,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
         const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
         uint32_t wl = 0;
+        Trace tr = make_trace(p.trace, 4, (warp & 3) == 0 && lane == 0);
         Step s;
         for (;;) {
             const int ev = gen.next(s);
             if (ev == 2) break;
             if (ev == 1 || !s.first_sub) continue;
+            tr.mark(30, wl);
             // 64 TMEM columns (16 16-byte loads, 64 registers) per round: 512 threads leave 128 registers per thread, so the 128
             // columns of an fp32 (hi | lo') weight buffer go in two rounds; the first round's loads are issued before the
             // buffer's release is awaited (the loaders run up to two groups ahead of the MMAs)
@@ -552,7 +585,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             };
             load_round(0);
             const uint32_t wb = wl & 1;
+            tr.mark(31, wl);
             mbar_wait(&w_empty[wb], ((wl >> 1) & 1) ^ 1);        // the MMAs that read this buffer two loads ago are done
+            tr.mark(32, wl);
             tc::tc_fence_after_sync();
 #pragma unroll
             for (int r = 0; r < NROUNDS; ++r) {
@@ -571,6 +606,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             tc::tmem_st_wait();
             tc::tc_fence_before_sync();
             mbar_arrive(&w_full[wb]);
+            tr.mark(33, wl);
             ++wl;
         }
     }
@@ -735,6 +771,16 @@ static int launch_seg(const Params &p, int use_target, cudaStream_t st) {
     return use_target ? launch_red<NPROD, K, 2>(p, st) : launch_red<NPROD, K, 1>(p, st);
 }
 
+static unsigned long long *g_trace_dev = nullptr;
+static unsigned long long *trace_buffer() {
+    static int want = -1;
+    if (want < 0) { const char *e = getenv("PTGNN_FUSED_TRACE"); want = (e && e[0] == '1') ? 1 : 0; }
+    if (!want) return nullptr;
+    if (!g_trace_dev && cudaMalloc(&g_trace_dev, 5 * 2048 * 8) != cudaSuccess) return nullptr;
+    cudaMemset(g_trace_dev, 0, 5 * 2048 * 8);
+    return g_trace_dev;
+}
+
 int aggregate(const AggregateArgs &a, cudaStream_t st) {
     PTGNN_CHECK_ARG(supported(a.nprod, a.K, kD, a.use_target), "fused aggregate: unsupported nprod=%d K=%d", a.nprod, a.K);
     PTGNN_CHECK_ARG(a.block_targets >= 8 && a.block_targets <= kMaxBlockTargets, "fused aggregate: block_targets=%d out of [8, %d]",
@@ -753,6 +799,7 @@ int aggregate(const AggregateArgs &a, cudaStream_t st) {
     p.out = a.out; p.num_nodes = (int)a.num_nodes; p.B = a.block_targets;
     p.num_blocks = (int)ceil_div(a.num_nodes, a.block_targets);
     p.T = a.num_types; p.reduce = a.reduce; p.out_mode = a.out_mode; p.status = a.status; p.epi = a.epi;
+    p.trace = trace_buffer();
     if (a.nprod == 3) {
         if (a.K == 64) return launch_seg<3, 64>(p, a.use_target, st);
         return launch_seg<3, 128>(p, a.use_target, st);
@@ -764,3 +811,11 @@ int aggregate(const AggregateArgs &a, cudaStream_t st) {
 
 }  // namespace fused
 }  // namespace ptgnn
+
+// debug only (not part of the public header): copies the last fused-kernel timeline (5 roles x 2048 entries) to `out`; 0 if tracing is off
+extern "C" int ptgnn_b200_debug_fused_trace(unsigned long long *out) {
+    if (!ptgnn::fused::g_trace_dev) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, ptgnn::fused::g_trace_dev, 5 * 2048 * 8, cudaMemcpyDeviceToHost);
+    return 1;
+}

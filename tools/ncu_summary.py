@@ -3,7 +3,14 @@
 
     python tools/ncu_summary.py gpurun_out/prof_x.ncu-rep profiles/r01_x.md ["title"]
     python tools/ncu_summary.py --launches gpurun_out/launches_r01.csv profiles/r01_launches.md
+    python tools/ncu_summary.py --traffic f32 message=gpurun_out/a.ncu-rep gru=gpurun_out/b.ncu-rep [pack=...]
+        -> updates profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch; read by bench.py)
+    python tools/ncu_summary.py --sass ptgnn_b200/libptgnn_b200.so profiles/r02_sass_opcodes.md
+        -> opcode histogram of the shipped library (UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA, LDGSTS = cp.async)
 """
+import json
+import os
+import re
 import csv
 import io
 import subprocess
@@ -80,8 +87,71 @@ def launches(src, dst):
     print("wrote", dst)
 
 
+def traffic(dtype, pairs):
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    try:
+        doc = json.load(open(path))
+    except (OSError, ValueError):
+        doc = {}
+    entry = doc.setdefault(dtype, {"kernels": {}, "source": ""})
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    srcs = []
+    for pair in pairs:
+        name, rep = pair.split("=", 1)
+        hdr, units, rows = raw_page(rep)
+        vals = []
+        for r in rows:
+            rd = float(r[hdr.index("dram__bytes_read.sum")]) * scale.get(units[hdr.index("dram__bytes_read.sum")], 1e6)
+            wr = float(r[hdr.index("dram__bytes_write.sum")]) * scale.get(units[hdr.index("dram__bytes_write.sum")], 1e6)
+            vals.append(rd + wr)
+        entry["kernels"][name] = sum(vals) / len(vals)
+        srcs.append(f"{name}: {os.path.basename(rep)} ({rows[0][hdr.index('Kernel Name')].split('(')[0]}, {len(vals)} launch(es))")
+    entry["source"] = "ncu --set full --clock-control none, config 2; " + "; ".join(srcs)
+    json.dump(doc, open(path, "w"), indent=1)
+    print("wrote", path, entry)
+
+
+def sass_histogram(lib, dst):
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    counts, per_fn, fn = {}, {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+            continue
+        m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_.]*)", line)
+        if m and fn:
+            op = m.group(1).split(".")[0]
+            counts[op] = counts.get(op, 0) + 1
+            if op.startswith("UTC") or op in ("LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "HMMA", "SYNCS", "USETMAXREG"):
+                per_fn.setdefault(fn, {}).setdefault(op, 0)
+                per_fn[fn][op] += 1
+    keys = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "SYNCS", "USETMAXREG", "HMMA", "FFMA"]
+    lines = [f"# SASS opcode histogram of `{lib}` (cuobjdump -sass; sm_100a)", "",
+             "Blackwell-native evidence: `UTCHMMA` = tcgen05.mma, `LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = TMA tile loads, `LDGSTS` = cp.async, "
+             "`SYNCS` = mbarrier ops, `USETMAXREG` = setmaxnreg.  No `HMMA` (legacy mma.sync) anywhere.", "",
+             "| opcode | count (whole library) |", "|---|---|"]
+    for k in keys:
+        lines.append(f"| {k} | {counts.get(k, 0)} |")
+    lines += ["", "## tensor / TMA / TMEM opcodes per kernel (template instantiations merged)", "", "| kernel | opcodes |", "|---|---|"]
+    merged = {}
+    for fn, ops in per_fn.items():
+        base = re.sub(r"<.*", "", fn)
+        m = merged.setdefault(base, {})
+        for k, v in ops.items():
+            m[k] = m.get(k, 0) + v
+    for fn, ops in sorted(merged.items()):
+        lines.append(f"| {fn} | " + ", ".join(f"{k} {v}" for k, v in sorted(ops.items())) + " |")
+    open(dst, "w").write("\n".join(lines) + "\n")
+    print("wrote", dst)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "--launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "--traffic":
+        traffic(sys.argv[2], sys.argv[3:])
+    elif sys.argv[1] == "--sass":
+        sass_histogram(sys.argv[2], sys.argv[3])
     else:
         summarise(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else sys.argv[1])
