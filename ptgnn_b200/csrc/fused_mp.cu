@@ -88,6 +88,25 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p) {
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ uint32_t swz(int row, int q) { return (uint32_t)(row * 128 + ((q ^ (row & 7)) << 4)); }
 
+// Up to 32 mbarriers polled by ONE try_wait instruction per round: lane i checks (addr, parity) of its own barrier (inactive lanes
+// report done).  A phase check costs ~200 cycles even when the barrier is already complete (measured, tools/fused_trace.py), so
+// the MMA warp's three per-step waits (accumulator drained, rows landed, weights landed) are folded into one.
+__device__ __forceinline__ void mbar_wait_lanes(uint32_t addr, uint32_t parity, bool active) {
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done = 1;
+        if (active)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (__all_sync(0xffffffffu, done != 0)) return;
+        if ((spin & 0xFF) == 0xFF) {
+            const uint64_t now = tc::global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+
 // Debug timeline (PTGNN_FUSED_TRACE=1): CTA 0, one thread per role, records (clock64, step, tag) at the pipeline hand-offs into its
 // 2048-entry region of the trace buffer; read back with ptgnn_b200_debug_fused_trace (tools/fused_trace.py).
 struct Trace {
@@ -248,15 +267,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 if (s.first_sub && s.seg == 0) { wl0 = wl; wl += NSEG; }
                 const uint32_t ab = sg & 1;
                 tr.mark(10, xs);
-                if (s.seg == 0) {
-                    mbar_wait(&acc_empty[ab], ((sg >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator set
-                }
-                tr.mark(11, xs);
                 const uint32_t slot = xs % NUM_SLOTS;
-                mbar_wait(&x_full[slot], (xs / NUM_SLOTS) & 1);
                 const uint32_t wli = wl0 + s.seg, wb = wli & 1;
-                tr.mark(12, xs);
-                if (s.first_sub) mbar_wait(&w_full[wb], (wli >> 1) & 1);
+                {   // lane 0: the epilogue has drained this accumulator set | lane 1: the rows have landed | lane 2: the weights have
+                    const uint32_t addr = lane == 0 ? smem_u32(&acc_empty[ab]) : (lane == 1 ? smem_u32(&x_full[slot]) : smem_u32(&w_full[wb]));
+                    const uint32_t parity = lane == 0 ? (((sg >> 1) & 1) ^ 1) : (lane == 1 ? ((xs / NUM_SLOTS) & 1) : ((wli >> 1) & 1));
+                    const bool active = lane == 0 ? s.seg == 0 : (lane == 1 ? true : (lane == 2 && s.first_sub));
+                    mbar_wait_lanes(addr, parity, active);
+                }
                 tr.mark(13, xs);
                 tc::tc_fence_after_sync();
                 const uint32_t n16 = (uint32_t)(s.n + 15) & ~15u;
@@ -445,11 +463,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 int split = __popc(m->lowmask[0]) + __popc(m->lowmask[1]);
                 if (NMAX > 64) split += __popc(m->lowmask[2]) + __popc(m->lowmask[3]);
                 const int c_lo = eg == 0 ? 0 : split, c_hi = eg == 0 ? split : n;       // this group's columns
+                constexpr int W = 16;
+                uint32_t nm[W], nc[W];                       // accumulator columns of the NEXT batch, loading while this one is processed
+                if ((c_lo & ~15) < c_hi) {
+                    tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + (c_lo & ~15), nm);
+                    if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + (c_lo & ~15), nc);
+                }
                 for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
-                    constexpr int W = 16;
-                    uint32_t vm[W], vc[W];
-                    tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
-                    if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
                     uint32_t addr[W];
 #pragma unroll
                     for (int j = 0; j < W / 4; ++j) {
@@ -468,6 +488,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
 #pragma unroll
                     for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
                     tc::tmem_ld_wait();
+                    uint32_t vm[W], vc[W];
+#pragma unroll
+                    for (int c = 0; c < W; ++c) { vm[c] = nm[c]; if (NPROD == 3) vc[c] = nc[c]; }
+                    if (c0 + 16 < c_hi) {
+                        tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0 + 16, nm);
+                        if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0 + 16, nc);
+                    }
                     // t[c] = op(pre[c], v[c]) for every column (independent); a column that CONTINUES a segment (rare: most
                     // (target, type) segments hold one edge) then overwrites it with op(t[c-1], v[c]) -- a predicated op, in
                     // column order, so a target's messages are still combined one by one in plan order.  Columns of the other
@@ -500,8 +527,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             named_bar_sync(EPI_BAR_ID, EPI_THREADS);
             const int row0 = s.blk * p.B;
             const int rows = min(p.B, p.num_nodes - row0);
-            for (int r = eg * 4 + ew; r < rows; r += 8) {
-                float4 a = *reinterpret_cast<const float4 *>(agg_s + r * kD + lane * 4);
+            auto finish_row = [&](int r, float4 a) {
                 const int v = row0 + r;
                 if (RED == PTGNN_REDUCE_MEAN) {
                     const int cnt = __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
@@ -548,9 +574,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 } else {
                     reinterpret_cast<float4 *>(p.out)[(size_t)v * (kD / 4) + lane] = a;
                 }
+            };
+            // 4 rows per iteration (independent loads in flight); a row is reset to the identity as soon as it has been read,
+            // so the next block needs no separate initialisation pass
+            const float4 ident4 = make_float4(IDENT, IDENT, IDENT, IDENT);
+            for (int r0 = eg * 4 + ew; r0 < rows; r0 += 32) {
+                float4 v4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + 8 * u;
+                    if (r < rows) {
+                        float4 *rowp = reinterpret_cast<float4 *>(agg_s + r * kD + lane * 4);
+                        v4[u] = *rowp;
+                        *rowp = ident4;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + 8 * u < rows) finish_row(r0 + 8 * u, v4[u]);
             }
             named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-            for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
             tr.mark(24, sg);
         }
     } else {
