@@ -29,7 +29,9 @@ constexpr int SLOT_BYTES = 32768;
 constexpr int RING_BYTES = NUM_SLOTS * SLOT_BYTES;
 constexpr int META_RING = 8;
 constexpr int SCHED_RING = 4;
-constexpr int W_REGS = 184, MID_REGS = 72;        // 512 threads launch with 128 registers each; warps 4-7 give 56 back, the weight loaders take them: (184 + 72 + 128 + 128) * 128 = 65536
+// 512 threads launch with 128 registers each; warps 4-7 and the weight loaders give registers back, the two epilogue warpgroups take them:
+// (2 * 160 + 72 + 120) * 128 = 65536.  ptxas only extends a role's budget beyond the launch cap when that role is the LAST branch.
+constexpr int EPI_REGS = 160, W_REGS = 120, MID_REGS = 72;
 constexpr int ACC_TMEM_OFF = 256;                               // weight buffers below, accumulators above
 constexpr int EPI_BAR_ID = 2;
 
@@ -178,6 +180,14 @@ __device__ __forceinline__ void continue_segment(float &t, float prev, float v, 
 __device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, uint32_t bit) {
     asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.u32 pe, %2, 0;\n\t@pe st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v), "r"(bit) : "memory");
 }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -204,6 +214,98 @@ template <int RED> __device__ __forceinline__ float red_op(float a, float m) {
 }
 
 // =====================================================================================================================
+// Write-out of a finished block: rows [row_lo, min(row_hi, rows of the block)) of agg_s, taken by the calling warp (ew of the four
+// of its group) 2 rows at a time; a row is reset to the identity as soon as it has been read.  The row loop is specialised at compile
+// time on the output format and on "plain sum" (no mean / max fix-up / activation / LayerNorm): the generic version executed ~180
+// instructions per row.  Register pressure matters here: the epilogue's column loop sits at the 128-register limit, and a 4-row
+// unroll (or a non-inlined call: ABI-constrained allocation) made ptxas spill around every LDTM of the column loop -- drain time
+// per sub-group went from 1,200 to 2,300 cycles (sessions r02g/r02h) -- so check `-Xptxas -v` for 0 spills after touching this.
+template <int RED>
+__device__ __forceinline__ void write_out_block(const Params *p, uint32_t agg_saddr, int row0, int row_lo, int row_hi, int ew, int lane) {
+    const float IDENT = red_identity<RED>();
+    const int rows = min(p->B, p->num_nodes - row0);
+    const int my_hi = min(row_hi, rows);
+    const float4 ident4 = make_float4(IDENT, IDENT, IDENT, IDENT);
+    auto finish_row = [&](auto mode_tag, auto plain_tag, int r, float4 a) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        constexpr bool PLAIN = decltype(plain_tag)::value;
+        const int v = row0 + r;
+        if (!PLAIN) {
+            if (RED == PTGNN_REDUCE_MEAN) {
+                const int cnt = __ldg(p->row_ptr + v + 1) - __ldg(p->row_ptr + v);
+                const float c = (float)(cnt < 1 ? 1 : cnt);
+                a.x /= c; a.y /= c; a.z /= c; a.w /= c;
+            }
+            if (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN) {   // never updated -> 0 (torch_scatter)
+                if (a.x == IDENT) a.x = 0.0f;
+                if (a.y == IDENT) a.y = 0.0f;
+                if (a.z == IDENT) a.z = 0.0f;
+                if (a.w == IDENT) a.w = 0.0f;
+            }
+            if (p->epi.act != PTGNN_ACT_NONE) {
+                a.x = apply_act(a.x, p->epi.act); a.y = apply_act(a.y, p->epi.act);
+                a.z = apply_act(a.z, p->epi.act); a.w = apply_act(a.w, p->epi.act);
+            }
+            if (p->epi.ln_w != nullptr) {       // LayerNorm over the 128 features of the row (same order as reduce.cuh)
+                float sum = (a.x + a.y) + (a.z + a.w);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float mean = sum / (float)kD;
+                const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
+                float qq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                const float rstd = rsqrtf(qq / (float)kD + p->epi.ln_eps);
+                const float4 w = *reinterpret_cast<const float4 *>(p->epi.ln_w + lane * 4);
+                const float4 b = *reinterpret_cast<const float4 *>(p->epi.ln_b + lane * 4);
+                a.x = dx * rstd * w.x + b.x; a.y = dy * rstd * w.y + b.y;
+                a.z = dz * rstd * w.z + b.z; a.w = dw * rstd * w.w + b.w;
+            }
+        }
+        if (MODE == 1) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&lo); pk.y = *reinterpret_cast<uint32_t *>(&hi);
+            reinterpret_cast<uint2 *>(p->out)[(size_t)v * (kD / 4) + lane] = pk;
+        } else if (MODE == 2) {      // fp16 (hi | lo') row: hi halfs at [0, 128), lo' halfs at [128, 256); packed conversions
+            const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn((a.x - f01.x) * 2048.0f, (a.y - f01.y) * 2048.0f);
+            const __half2 l23 = __floats2half2_rn((a.z - f23.x) * 2048.0f, (a.w - f23.y) * 2048.0f);
+            uint2 *row = reinterpret_cast<uint2 *>(p->out) + (size_t)v * (2 * kD / 4);
+            row[lane] = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+            row[kD / 4 + lane] = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+            const float big = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+            if (!(big < 65504.0f) && p->status != nullptr) *reinterpret_cast<volatile int32_t *>(p->status) = 1;
+        } else {
+            reinterpret_cast<float4 *>(p->out)[(size_t)v * (kD / 4) + lane] = a;
+        }
+    };
+    // 2 rows per iteration (independent loads in flight); rows are reset as they are read: the next block needs no initialisation pass
+    auto write_rows = [&](auto mode_tag, auto plain_tag) {
+        for (int r0 = row_lo + ew; r0 < my_hi; r0 += 4 * 2) {
+            float4 v4[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = r0 + 4 * u;
+                if (r < my_hi) {
+                    const uint32_t rowa = agg_saddr + (uint32_t)(r * kD + lane * 4) * 4u;
+                    v4[u] = lds_f32x4(rowa);
+                    sts_f32x4(rowa, ident4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (r0 + 4 * u < my_hi) finish_row(mode_tag, plain_tag, r0 + 4 * u, v4[u]);
+        }
+    };
+    const bool plain = RED == PTGNN_REDUCE_SUM && p->epi.act == PTGNN_ACT_NONE && p->epi.ln_w == nullptr;
+    using std::integral_constant;
+    if (p->out_mode == 2) { if (plain) write_rows(integral_constant<int, 2>{}, integral_constant<bool, true>{}); else write_rows(integral_constant<int, 2>{}, integral_constant<bool, false>{}); }
+    else if (p->out_mode == 1) { if (plain) write_rows(integral_constant<int, 1>{}, integral_constant<bool, true>{}); else write_rows(integral_constant<int, 1>{}, integral_constant<bool, false>{}); }
+    else { if (plain) write_rows(integral_constant<int, 0>{}, integral_constant<bool, true>{}); else write_rows(integral_constant<int, 0>{}, integral_constant<bool, false>{}); }
+}
+
 template <int NPROD, int K, int NSEG, int RED>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const __grid_constant__ Params p) {
     constexpr int NPART = NPROD == 3 ? 2 : 1;                      // hi | lo' parts of a row / of the weights
@@ -428,190 +530,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             }
             cp_async_wait<0>();
         }
-    } else if (warp < 12) {
-        // ============================================ EPILOGUE ============================================
-        // Thread d owns message feature d = TMEM lane d and column d of agg_s.  For every accumulator column (edge) in plan
-        // order: value = main (+ 2^-11 correction); at the first edge of a (target, type) segment the running value is
-        // (re)loaded from agg_s[target][d], at the last one it is stored back -- a target's messages are accumulated one by one
-        // in the reference's order, across types and sub-groups.
-        // TWO warpgroups (a single warp per scheduler is latency-bound: measured IPC 0.17): group 0 takes the columns whose
-        // target lies in the lower half of the block, group 1 the upper half.  Edges are sorted by target, so each group owns a
-        // contiguous column range of every sub-group (split = number of lower-half columns) and the two never touch the same
-        // agg_s row -- no synchronisation between them except at the block's write-out.
-        const int eg = warp >> 3, ew = warp & 3;             // warps 0-3: group 0, warps 8-11: group 1
-        const int d = ew * 32 + lane;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC_TMEM_OFF;
-        const uint32_t aggcol_s = smem_u32(agg_s + d);      // shared-space address of agg_s[0][d]
-        const float IDENT = red_identity<RED>();
-        StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
-        const int row_lo = eg == 0 ? 0 : (p.B >> 1), row_hi = eg == 0 ? (p.B >> 1) : p.B;     // rows this group initialises
-        for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
-        uint32_t sg = 0;
-        float acc = IDENT;
-        Trace tr = make_trace(p.trace, 2 + eg, ew == 0 && lane == 0);
-        Step s;
-        for (;;) {
-            const int ev = gen.next(s);
-            if (ev == 2) break;
-            if (ev == 0) {
-                if (s.seg != NSEG - 1) continue;
-                const uint32_t ab = sg & 1;
-                tr.mark(20, sg);
-                mbar_wait(&acc_full[ab], (sg >> 1) & 1);
-                tr.mark(21, sg);
-                tc::tc_fence_after_sync();
-                const Meta *m = &meta_ring[sg % META_RING];
-                const int n = s.n;
-                int split = __popc(m->lowmask[0]) + __popc(m->lowmask[1]);
-                if (NMAX > 64) split += __popc(m->lowmask[2]) + __popc(m->lowmask[3]);
-                const int c_lo = eg == 0 ? 0 : split, c_hi = eg == 0 ? split : n;       // this group's columns
-                constexpr int W = 16;
-                for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
-                    uint32_t vm[W], vc[W];
-                    tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
-                    if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
-                    uint32_t addr[W];
-#pragma unroll
-                    for (int j = 0; j < W / 4; ++j) {
-                        const int4 o = *reinterpret_cast<const int4 *>(&m->tloff[c0 + 4 * j]);
-                        addr[4 * j] = aggcol_s + o.x; addr[4 * j + 1] = aggcol_s + o.y;
-                        addr[4 * j + 2] = aggcol_s + o.z; addr[4 * j + 3] = aggcol_s + o.w;
-                    }
-                    const uint32_t endw = (m->endmask[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
-                    // the column before this batch ended a segment (or the batch opens the sub-group: always reload)
-                    const uint32_t prev_end = c0 == 0 ? 1u : (m->endmask[(c0 - 1) >> 5] >> ((c0 - 1) & 31)) & 1u;
-                    const uint32_t startw = (endw << 1) | prev_end;
-                    // columns of the batch that belong to this group: [max(c_lo, c0), min(c_hi, c0 + 16))
-                    const int first = c_lo > c0 ? c_lo - c0 : 0, last = c_hi - c0 < W ? c_hi - c0 : W;
-                    const uint32_t storew = endw & (0xFFFFu << first) & (0xFFFFu >> (W - last));
-                    float pre[W];
-#pragma unroll
-                    for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
-                    tc::tmem_ld_wait();
-                    // t[c] = op(pre[c], v[c]) for every column (independent); a column that CONTINUES a segment (rare: most
-                    // (target, type) segments hold one edge) then overwrites it with op(t[c-1], v[c]) -- a predicated op, in
-                    // column order, so a target's messages are still combined one by one in plan order.  Columns of the other
-                    // group are computed but never stored; this group's first column always starts a segment.
-                    float t[W];
-#pragma unroll
-                    for (int c = 0; c < W; ++c) {
-                        float v = __uint_as_float(vm[c]);
-                        if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
-                        else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
-                        vm[c] = __float_as_uint(v);
-                        t[c] = red_op<RED>(pre[c], v);
-                    }
-                    continue_segment<RED>(t[0], acc, __uint_as_float(vm[0]), startw & 1u);
-#pragma unroll
-                    for (int c = 1; c < W; ++c) continue_segment<RED>(t[c], t[c - 1], __uint_as_float(vm[c]), startw & (1u << c));
-                    acc = t[W - 1];
-#pragma unroll
-                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], t[c], storew & (1u << c));
-                }
-                tc::tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[ab]);
-                tr.mark(22, sg);
-                ++sg;
-                continue;
-            }
-            // ---- block finished.  Each group writes out ITS half of the rows as soon as its own four warps are done (no waiting for
-            // the other group).  The row loop is specialised at compile time on the output format and on "plain sum" (no mean /
-            // max fix-up / activation / LayerNorm): the generic version executed ~180 instructions per row, 13,600 cycles per block.
-            tr.mark(23, sg);
-            named_bar_sync(EPI_BAR_ID + eg, 128);
-            const int row0 = s.blk * p.B;
-            const int rows = min(p.B, p.num_nodes - row0);
-            const int my_hi = min(row_hi, rows);
-            const float4 ident4 = make_float4(IDENT, IDENT, IDENT, IDENT);
-            auto finish_row = [&](auto mode_tag, auto plain_tag, int r, float4 a) {
-                constexpr int MODE = decltype(mode_tag)::value;
-                constexpr bool PLAIN = decltype(plain_tag)::value;
-                const int v = row0 + r;
-                if (!PLAIN) {
-                    if (RED == PTGNN_REDUCE_MEAN) {
-                        const int cnt = __ldg(p.row_ptr + v + 1) - __ldg(p.row_ptr + v);
-                        const float c = (float)(cnt < 1 ? 1 : cnt);
-                        a.x /= c; a.y /= c; a.z /= c; a.w /= c;
-                    }
-                    if (RED == PTGNN_REDUCE_MAX || RED == PTGNN_REDUCE_MIN) {   // never updated -> 0 (torch_scatter)
-                        if (a.x == IDENT) a.x = 0.0f;
-                        if (a.y == IDENT) a.y = 0.0f;
-                        if (a.z == IDENT) a.z = 0.0f;
-                        if (a.w == IDENT) a.w = 0.0f;
-                    }
-                    if (p.epi.act != PTGNN_ACT_NONE) {
-                        a.x = apply_act(a.x, p.epi.act); a.y = apply_act(a.y, p.epi.act);
-                        a.z = apply_act(a.z, p.epi.act); a.w = apply_act(a.w, p.epi.act);
-                    }
-                    if (p.epi.ln_w != nullptr) {       // LayerNorm over the 128 features of the row (same order as reduce.cuh)
-                        float sum = (a.x + a.y) + (a.z + a.w);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                        const float mean = sum / (float)kD;
-                        const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
-                        float qq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-                        const float rstd = rsqrtf(qq / (float)kD + p.epi.ln_eps);
-                        const float4 w = *reinterpret_cast<const float4 *>(p.epi.ln_w + lane * 4);
-                        const float4 b = *reinterpret_cast<const float4 *>(p.epi.ln_b + lane * 4);
-                        a.x = dx * rstd * w.x + b.x; a.y = dy * rstd * w.y + b.y;
-                        a.z = dz * rstd * w.z + b.z; a.w = dw * rstd * w.w + b.w;
-                    }
-                }
-                if (MODE == 1) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<uint32_t *>(&lo); pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                    reinterpret_cast<uint2 *>(p.out)[(size_t)v * (kD / 4) + lane] = pk;
-                } else if (MODE == 2) {      // fp16 (hi | lo') row: hi halfs at [0, 128), lo' halfs at [128, 256); packed conversions
-                    const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    const __half2 l01 = __floats2half2_rn((a.x - f01.x) * 2048.0f, (a.y - f01.y) * 2048.0f);
-                    const __half2 l23 = __floats2half2_rn((a.z - f23.x) * 2048.0f, (a.w - f23.y) * 2048.0f);
-                    uint2 *row = reinterpret_cast<uint2 *>(p.out) + (size_t)v * (2 * kD / 4);
-                    row[lane] = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
-                    row[kD / 4 + lane] = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
-                    const float big = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-                    if (!(big < 65504.0f) && p.status != nullptr) *reinterpret_cast<volatile int32_t *>(p.status) = 1;
-                } else {
-                    reinterpret_cast<float4 *>(p.out)[(size_t)v * (kD / 4) + lane] = a;
-                }
-            };
-            // 4 rows per iteration (independent loads in flight); a row is reset to the identity as soon as it has been read, so the
-            // next block needs no separate initialisation pass
-            auto write_rows = [&](auto mode_tag, auto plain_tag) {
-                for (int r0 = row_lo + ew; r0 < my_hi; r0 += 16) {
-                    float4 v4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = r0 + 4 * u;
-                        if (r < my_hi) {
-                            float4 *rowp = reinterpret_cast<float4 *>(agg_s + r * kD + lane * 4);
-                            v4[u] = *rowp;
-                            *rowp = ident4;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (r0 + 4 * u < my_hi) finish_row(mode_tag, plain_tag, r0 + 4 * u, v4[u]);
-                }
-            };
-            const bool plain = RED == PTGNN_REDUCE_SUM && p.epi.act == PTGNN_ACT_NONE && p.epi.ln_w == nullptr;
-            using std::integral_constant;
-            if (p.out_mode == 2) { if (plain) write_rows(integral_constant<int, 2>{}, integral_constant<bool, true>{}); else write_rows(integral_constant<int, 2>{}, integral_constant<bool, false>{}); }
-            else if (p.out_mode == 1) { if (plain) write_rows(integral_constant<int, 1>{}, integral_constant<bool, true>{}); else write_rows(integral_constant<int, 1>{}, integral_constant<bool, false>{}); }
-            else { if (plain) write_rows(integral_constant<int, 0>{}, integral_constant<bool, true>{}); else write_rows(integral_constant<int, 0>{}, integral_constant<bool, false>{}); }
-            named_bar_sync(EPI_BAR_ID + eg, 128);
-            tr.mark(24, sg);
-        }
-    } else {
+    } else if (warp >= 12) {
         // ============================================ WEIGHT LOADERS ============================================
         // Thread d owns TMEM lane d = row d of W_t.  The packed weights are laid out so that a warp-wide 16-byte load is one
         // contiguous 512-byte burst: wpack[(((t * NSEG + seg) * NPART + part) * (K / 8) + c4) * 128 + d] = columns 4 c4 .. 4 c4 + 3.
         // All loads of a (type, segment) are in flight before the buffer's release is awaited.
-        tc::reg_alloc<W_REGS>();                   // granted once warps 4-7 have released theirs
+        tc::reg_dealloc<W_REGS>();
         const int d = (warp & 3) * 32 + lane;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
@@ -626,7 +550,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             // 64 TMEM columns (16 16-byte loads, 64 registers) per round: 512 threads leave 128 registers per thread, so the 128
             // columns of an fp32 (hi | lo') weight buffer go in two rounds; the first round's loads are issued before the
             // buffer's release is awaited (the loaders run up to two groups ahead of the MMAs)
-            constexpr int ROUND = WBUF_COLS, NROUNDS = 1;          // all of a buffer's loads in flight at once (W_REGS registers)
+            constexpr int ROUND = WBUF_COLS < 64 ? WBUF_COLS : 64, NROUNDS = WBUF_COLS / ROUND;
             const uint4 *src = p.wpack + ((size_t)(s.t * NSEG + s.seg) * NPART * (K / 8)) * 128 + d;
             uint32_t w[ROUND];
             auto load_round = [&](int r) {
@@ -661,6 +585,109 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
             mbar_arrive(&w_full[wb]);
             tr.mark(33, wl);
             ++wl;
+        }
+    } else {
+        // ============================================ EPILOGUE ============================================
+        // Thread d owns message feature d = TMEM lane d and column d of agg_s.  For every accumulator column (edge) in plan
+        // order: value = main (+ 2^-11 correction); at the first edge of a (target, type) segment the running value is
+        // (re)loaded from agg_s[target][d], at the last one it is stored back -- a target's messages are accumulated one by one
+        // in the reference's order, across types and sub-groups.
+        // TWO warpgroups (a single warp per scheduler is latency-bound: measured IPC 0.17): group 0 takes the columns whose
+        // target lies in the lower half of the block, group 1 the upper half.  Edges are sorted by target, so each group owns a
+        // contiguous column range of every sub-group (split = number of lower-half columns) and the two never touch the same
+        // agg_s row -- no synchronisation between them except at the block's write-out.
+        tc::reg_alloc<EPI_REGS>();                 // granted once warps 4-7 and 12-15 have released theirs
+        const int eg = warp >> 3, ew = warp & 3;             // warps 0-3: group 0, warps 8-11: group 1
+        const int d = ew * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + ACC_TMEM_OFF;
+        const uint32_t aggcol_s = smem_u32(agg_s + d);      // shared-space address of agg_s[0][d]
+        const float IDENT = red_identity<RED>();
+        StepGen<NSEG> gen{sched, sched_full, sched_empty, T, NMAX, lane};
+        const int row_lo = eg == 0 ? 0 : (p.B >> 1), row_hi = eg == 0 ? (p.B >> 1) : p.B;     // rows this group initialises
+        for (int r = row_lo; r < row_hi; ++r) agg_s[r * kD + d] = IDENT;
+        uint32_t sg = 0;
+        float acc = IDENT;
+        Trace tr = make_trace(p.trace, 2 + eg, ew == 0 && lane == 0);
+        Step s;
+        for (;;) {
+            const int ev = gen.next(s);
+            if (ev == 2) break;
+            if (ev == 0) {
+                if (s.seg != NSEG - 1) continue;
+                const uint32_t ab = sg & 1;
+                tr.mark(20, sg);
+                mbar_wait(&acc_full[ab], (sg >> 1) & 1);
+                tr.mark(21, sg);
+                tc::tc_fence_after_sync();
+                const Meta *m = &meta_ring[sg % META_RING];
+                const int n = s.n;
+                int split = __popc(m->lowmask[0]) + __popc(m->lowmask[1]);
+                if (NMAX > 64) split += __popc(m->lowmask[2]) + __popc(m->lowmask[3]);
+                const int c_lo = eg == 0 ? 0 : split, c_hi = eg == 0 ? split : n;       // this group's columns
+                constexpr int W = 16;
+                for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
+                    uint32_t vm[W], vc[W];
+                    const bool tb = c0 == (c_lo & ~15);        // trace the first batch of the sub-group
+                    if (tb) tr.mark(25, sg);
+                    tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
+                    if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
+                    uint32_t addr[W];
+#pragma unroll
+                    for (int j = 0; j < W / 4; ++j) {
+                        const int4 o = *reinterpret_cast<const int4 *>(&m->tloff[c0 + 4 * j]);
+                        addr[4 * j] = aggcol_s + o.x; addr[4 * j + 1] = aggcol_s + o.y;
+                        addr[4 * j + 2] = aggcol_s + o.z; addr[4 * j + 3] = aggcol_s + o.w;
+                    }
+                    const uint32_t endw = (m->endmask[c0 >> 5] >> (c0 & 31)) & 0xFFFFu;
+                    // the column before this batch ended a segment (or the batch opens the sub-group: always reload)
+                    const uint32_t prev_end = c0 == 0 ? 1u : (m->endmask[(c0 - 1) >> 5] >> ((c0 - 1) & 31)) & 1u;
+                    const uint32_t startw = (endw << 1) | prev_end;
+                    // columns of the batch that belong to this group: [max(c_lo, c0), min(c_hi, c0 + 16))
+                    const int first = c_lo > c0 ? c_lo - c0 : 0, last = c_hi - c0 < W ? c_hi - c0 : W;
+                    const uint32_t storew = endw & (0xFFFFu << first) & (0xFFFFu >> (W - last));
+                    float pre[W];
+#pragma unroll
+                    for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
+                    if (tb) tr.mark(26, sg);
+                    tc::tmem_ld_wait();
+                    if (tb) tr.mark(27, sg);
+                    // t[c] = op(pre[c], v[c]) for every column (independent); a column that CONTINUES a segment (rare: most
+                    // (target, type) segments hold one edge) then overwrites it with op(t[c-1], v[c]) -- a predicated op, in
+                    // column order, so a target's messages are still combined one by one in plan order.  Columns of the other
+                    // group are computed but never stored; this group's first column always starts a segment.
+                    float t[W];
+#pragma unroll
+                    for (int c = 0; c < W; ++c) {
+                        float v = __uint_as_float(vm[c]);
+                        if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
+                        else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
+                        vm[c] = __float_as_uint(v);
+                        t[c] = red_op<RED>(pre[c], v);
+                    }
+                    continue_segment<RED>(t[0], acc, __uint_as_float(vm[0]), startw & 1u);
+#pragma unroll
+                    for (int c = 1; c < W; ++c) continue_segment<RED>(t[c], t[c - 1], __uint_as_float(vm[c]), startw & (1u << c));
+                    acc = t[W - 1];
+                    if (tb) tr.mark(28, sg);
+#pragma unroll
+                    for (int c = 0; c < W; ++c) sts_f32_if(addr[c], t[c], storew & (1u << c));
+                    if (tb) tr.mark(29, sg);
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                tr.mark(22, sg);
+                ++sg;
+                continue;
+            }
+            // ---- block finished.  Each group writes out ITS half of the rows as soon as its own four warps are done (no waiting for
+            // the other group).  The row loop is specialised at compile time on the output format and on "plain sum" (no mean /
+            // max fix-up / activation / LayerNorm): the generic version executed ~180 instructions per row, 13,600 cycles per block.
+            tr.mark(23, sg);
+            if (eg == 0) named_bar_sync(EPI_BAR_ID, 128); else named_bar_sync(EPI_BAR_ID + 1, 128);
+            write_out_block<RED>(&p, smem_u32(agg_s), s.blk * p.B, row_lo, row_hi, ew, lane);
+            if (eg == 0) named_bar_sync(EPI_BAR_ID, 128); else named_bar_sync(EPI_BAR_ID + 1, 128);
+            tr.mark(24, sg);
         }
     }
     tc::tc_fence_before_sync();
@@ -853,6 +880,9 @@ int aggregate(const AggregateArgs &a, cudaStream_t st) {
     p.num_blocks = (int)ceil_div(a.num_nodes, a.block_targets);
     p.T = a.num_types; p.reduce = a.reduce; p.out_mode = a.out_mode; p.status = a.status; p.epi = a.epi;
     p.trace = trace_buffer();
+#ifdef PTGNN_FUSED_QUICK   // compile-time experiments (ptxas -v / SASS of the benchmarked instances only); never defined in the build
+    return a.nprod == 3 ? launch_one<3, 128, 1, PTGNN_REDUCE_SUM>(p, st) : launch_one<1, 128, 1, PTGNN_REDUCE_SUM>(p, st);
+#else
     if (a.nprod == 3) {
         if (a.K == 64) return launch_seg<3, 64>(p, a.use_target, st);
         return launch_seg<3, 128>(p, a.use_target, st);
@@ -860,6 +890,7 @@ int aggregate(const AggregateArgs &a, cudaStream_t st) {
     if (a.K == 64) return launch_seg<1, 64>(p, a.use_target, st);
     if (a.K == 128) return launch_seg<1, 128>(p, a.use_target, st);
     return launch_seg<1, 256>(p, a.use_target, st);
+#endif
 }
 
 }  // namespace fused

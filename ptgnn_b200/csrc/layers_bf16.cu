@@ -440,23 +440,18 @@ static int debug_bits() {
     const char *e = getenv("PTGNN_TC_DEBUG");
     return e ? atoi(e) : 0;
 }
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
+static int sm_count() {   // of the CURRENT device: a process may drive several GPUs (nothing cached across devices)
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     return n;
 }
 template <class Policy>
 static int launch_pipeline(const typename Policy::Params &p, int total_tiles, int category, cudaStream_t st) {
     if (total_tiles <= 0) return PTGNN_OK;
-    static bool configured = false;
-    if (!configured) {
-        PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_bf16_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
-    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    // per launch, not once per process: the attribute is per device (and per context)
+    PTGNN_CUDA(cudaFuncSetAttribute(tc_pipeline_bf16_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int sms = sm_count();
+    const int grid = total_tiles < sms ? total_tiles : sms;
     {
         TimedScope timed__(category, st);
         tc_pipeline_bf16_kernel<Policy><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
