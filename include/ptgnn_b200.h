@@ -262,6 +262,25 @@ int ptgnn_b200_gated_forward_fused(int32_t bf16_states, const void *node_states,
                                    void *out_states, void *workspace, size_t workspace_bytes, void *weight_cache,
                                    size_t weight_cache_bytes, int32_t cache_valid, void *stream);
 
+/* The fp32 fused path computes on packed states: every fp32 state x as two fp16 numbers (hi | lo') in rows of 2 * state_dim
+ * halfs (ptgnn_b200_packed_state_bytes per tensor).  In a stack of layers (GraphNeuralNetwork.gnn,
+ * ptgnn/neuralmodels/gnn/graphneuralnetwork.py:121-131) the packing pass of layer i + 1 is redundant: the GRU kernel of layer i
+ * can write its new states in both forms.  ptgnn_b200_gated_forward_fused_chained = ptgnn_b200_gated_forward_fused for fp32
+ * states, plus
+ *   packed_states_in  (optional): the packed form of node_states, as written through packed_states_out by the previous layer;
+ *   packed_states_out (optional): [num_nodes] packed rows, receives the packed form of out_states (bit-identical to what the
+ *                                 next call would derive from out_states itself). */
+size_t ptgnn_b200_packed_state_bytes(int64_t num_nodes, int32_t state_dim);
+int ptgnn_b200_gated_forward_fused_chained(const float *node_states, const float *gather_states /* NULL: node_states */,
+                                           const void *packed_states_in, int64_t num_nodes, int64_t num_source_nodes,
+                                           int32_t state_dim, int32_t message_dim, int32_t num_types,
+                                           const ptgnn_b200_block_plan *block_plan, const int32_t *row_ptr,
+                                           const float *const *edge_weights /*[host] T device pointers, fp32*/,
+                                           const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih,
+                                           const float *gru_b_hh, int32_t reduce, float *out_states, void *packed_states_out,
+                                           void *workspace, size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                           int32_t cache_valid, void *stream);
+
 /* MlpMessagePassingLayer.forward through the fused kernel (contract of ptgnn_b200_mlp_forward_{f32,bf16}); the message
  * activation and the LayerNorm run in the fused kernel's write-out. */
 size_t ptgnn_b200_mlp_fused_workspace_bytes(int32_t bf16_states, int64_t num_nodes, int64_t num_source_nodes, int32_t num_types,

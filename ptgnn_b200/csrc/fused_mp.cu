@@ -627,8 +627,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                 constexpr int W = 16;
                 for (int c0 = c_lo & ~15; c0 < c_hi; c0 += 16) {
                     uint32_t vm[W], vc[W];
-                    const bool tb = c0 == (c_lo & ~15);        // trace the first batch of the sub-group
-                    if (tb) tr.mark(25, sg);
                     tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + c0, vm);
                     if (NPROD == 3) tc::tmem_ld_16cols_async(tmem_lane + ab * ACC_COLS + 64 + c0, vc);
                     uint32_t addr[W];
@@ -648,9 +646,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     float pre[W];
 #pragma unroll
                     for (int c = 0; c < W; ++c) pre[c] = lds_f32(addr[c]);
-                    if (tb) tr.mark(26, sg);
                     tc::tmem_ld_wait();
-                    if (tb) tr.mark(27, sg);
                     // t[c] = op(pre[c], v[c]) for every column (independent); a column that CONTINUES a segment (rare: most
                     // (target, type) segments hold one edge) then overwrites it with op(t[c-1], v[c]) -- a predicated op, in
                     // column order, so a target's messages are still combined one by one in plan order.  Columns of the other
@@ -668,10 +664,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
 #pragma unroll
                     for (int c = 1; c < W; ++c) continue_segment<RED>(t[c], t[c - 1], __uint_as_float(vm[c]), startw & (1u << c));
                     acc = t[W - 1];
-                    if (tb) tr.mark(28, sg);
 #pragma unroll
                     for (int c = 0; c < W; ++c) sts_f32_if(addr[c], t[c], storew & (1u << c));
-                    if (tb) tr.mark(29, sg);
                 }
                 tc::tc_fence_before_sync();
                 __syncwarp();

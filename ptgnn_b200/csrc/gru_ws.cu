@@ -45,6 +45,9 @@ struct Params {
     const __nv_bfloat16 *h16;            // NPROD 1
     const float4 *bias4;                 // (b_ir + b_hr, b_iz + b_hz, b_in, b_hn) per hidden unit
     void *out;                           // fp32 [N, H] (NPROD 3) or bf16 (NPROD 1)
+    __half *out_packed;                  // optional (NPROD 3): the new states also as fp16 (hi | lo') rows of 2H halfs -- what the next
+                                         // layer's fused aggregation and GRU take as MMA operands (saves its pack_states pass)
+    int32_t *status;                     // optional: status[0] = 1 if a new state is outside the fp16 range (out_packed only)
     int num_nodes, H, D, n_jb, n_rb;
 };
 
@@ -282,6 +285,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_ws_kernel(const __grid_con
                         float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + pre.off + 16 * half);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        if (p.out_packed != nullptr) {      // same split as pack_states: hi = rn16(x), lo' = rn16((x - hi) * 2^11)
+                            uint32_t hw[8], lw[8];
+                            float big = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __half2 h2 = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+                                const float2 f2 = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn((o[2 * i] - f2.x) * 2048.0f, (o[2 * i + 1] - f2.y) * 2048.0f);
+                                hw[i] = *reinterpret_cast<const uint32_t *>(&h2);
+                                lw[i] = *reinterpret_cast<const uint32_t *>(&l2);
+                                big = fmaxf(big, fmaxf(fabsf(o[2 * i]), fabsf(o[2 * i + 1])));
+                            }
+                            // row r = (off - 32 jb) / H holds 2H halfs: hi at [0, H), lo' at [H, 2H)
+                            __half *rowp = p.out_packed + 2 * (pre.off - jb * 32) + jb * 32 + 16 * half;
+                            uint4 *dh = reinterpret_cast<uint4 *>(rowp), *dl = reinterpret_cast<uint4 *>(rowp + p.H);
+                            dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); dh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                            dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                            if (!(big < 65504.0f) && p.status != nullptr) *reinterpret_cast<volatile int32_t *>(p.status) = 1;
+                        }
                     } else {
                         uint32_t w[8];
 #pragma unroll
@@ -412,8 +434,9 @@ int pack(int nprod, int H, int D, const float *w_ih, const float *w_hh, const fl
 }
 
 int update(int nprod, const void *agg_rows, const void *h_rows, const void *h_plain, int64_t num_nodes, int H, int D, const void *packed,
-           void *out, cudaStream_t st) {
+           void *out, void *out_packed, int32_t *status, cudaStream_t st) {
     PTGNN_CHECK_ARG(supported(nprod, H, D), "gru_ws: unsupported dims H=%d D=%d", H, D);
+    PTGNN_CHECK_ARG(out_packed == nullptr || nprod == 3, "gru_ws: packed output is an fp32-path (3xFP16) feature");
     if (num_nodes <= 0) return PTGNN_OK;
     const int npart = nprod == 3 ? 2 : 1;
     uint16_t *p1, *p2;
@@ -428,7 +451,7 @@ int update(int nprod, const void *agg_rows, const void *h_rows, const void *h_pl
     if (!rc) rc = make_map16(&p.map_p2, p2, npart * n_jb * 128, H, 128, bf);
     if (rc) return rc;
     p.h32 = static_cast<const float *>(h_plain); p.h16 = static_cast<const __nv_bfloat16 *>(h_plain);
-    p.bias4 = bias4; p.out = out; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = (int)n_jb;
+    p.bias4 = bias4; p.out = out; p.out_packed = static_cast<__half *>(out_packed); p.status = status; p.num_nodes = (int)num_nodes; p.H = H; p.D = D; p.n_jb = (int)n_jb;
     p.n_rb = (int)ceil_div(num_nodes, TILE_M);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;

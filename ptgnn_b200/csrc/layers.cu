@@ -377,7 +377,8 @@ static int gated_forward_impl(const float *node_states, const float *gather_stat
                               const float *gru_w_ih, const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
                               int32_t reduce, float *out_states, void *workspace, size_t workspace_bytes, void *weight_cache,
                               size_t weight_cache_bytes, int32_t cache_valid, void *stream,
-                              const ptgnn_b200_block_plan *bp = nullptr, int64_t num_source_nodes = 0) {
+                              const ptgnn_b200_block_plan *bp = nullptr, int64_t num_source_nodes = 0,
+                              const void *packed_in = nullptr, void *packed_out = nullptr) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int H = state_dim, D = message_dim;
     PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && (type_off || bp), "gated_forward: bad num_types=%d",
@@ -430,10 +431,18 @@ static int gated_forward_impl(const float *node_states, const float *gather_stat
             rc = fused::pack_weights(3, num_types, H, 0, edge_weights, wsplit, bp->status, st);
             if (rc) return rc;
         }
-        rc = fused::pack_states(gsrc, num_source_nodes, H, ws + L.xpack, bp->status, st);
-        if (rc) return rc;
+        // packed_in (optional): node_states already as fp16 (hi | lo') rows -- the previous layer's GRU wrote them next to its
+        // fp32 output -- so the packing pass is skipped.  In a sharded run the gathered rows are a different tensor: they are
+        // packed here, and packed_in (this rank's rows) feeds the GRU.
+        const bool sharded = gather_states != nullptr && gather_states != node_states;
+        const void *src_rows = packed_in;
+        if (sharded || packed_in == nullptr) {
+            rc = fused::pack_states(gsrc, num_source_nodes, H, ws + L.xpack, bp->status, st);
+            if (rc) return rc;
+            src_rows = ws + L.xpack;
+        }
         fused::AggregateArgs a{};
-        a.nprod = 3; a.src_rows = ws + L.xpack; a.tgt_rows = nullptr; a.num_nodes = num_nodes; a.K = H; a.num_types = num_types;
+        a.nprod = 3; a.src_rows = src_rows; a.tgt_rows = nullptr; a.num_nodes = num_nodes; a.K = H; a.num_types = num_types;
         a.use_target = 0; a.reduce = reduce; a.block_targets = bp->block_targets; a.group_off = bp->group_off; a.src_f = bp->src_f;
         a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = wsplit; a.epi = fused::Epilogue{PTGNN_ACT_NONE, nullptr, nullptr, 0.0f};
         a.status = bp->status;
@@ -441,20 +450,26 @@ static int gated_forward_impl(const float *node_states, const float *gather_stat
         a.out = agg; a.out_mode = ws_gru ? 2 : 0;
         rc = fused::aggregate(a, st);
         if (rc) return rc;
-        if (!ws_gru)
-            return tc::gru_update(agg, node_states, num_nodes, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, out_states, grupack, pack, st);
+        if (!ws_gru) {
+            rc = tc::gru_update(agg, node_states, num_nodes, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, out_states, grupack, pack, st);
+            if (rc || packed_out == nullptr) return rc;
+            return fused::pack_states(out_states, num_nodes, H, packed_out, bp->status, st);
+        }
         // 3. GRUCell, weights-stationary, on the packed aggregate and the packed states (3xFP16)
         if (pack) {
             rc = gruws::pack(3, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, grupack, st);
             if (rc) return rc;
         }
-        const void *h_rows = ws + L.xpack;
-        if (gather_states != nullptr && gather_states != node_states) {   // sharded run: the packed copy above holds the GATHERED rows; the GRU needs this rank's
-            rc = fused::pack_states(node_states, num_nodes, H, ws + L.xpack_own, bp->status, st);
-            if (rc) return rc;
-            h_rows = ws + L.xpack_own;
+        const void *h_rows = src_rows;
+        if (sharded) {      // the packed copy above holds the GATHERED rows; the GRU needs this rank's
+            h_rows = packed_in;
+            if (h_rows == nullptr) {
+                rc = fused::pack_states(node_states, num_nodes, H, ws + L.xpack_own, bp->status, st);
+                if (rc) return rc;
+                h_rows = ws + L.xpack_own;
+            }
         }
-        return gruws::update(3, agg, h_rows, node_states, num_nodes, H, D, grupack, out_states, st);
+        return gruws::update(3, agg, h_rows, node_states, num_nodes, H, D, grupack, out_states, packed_out, bp->status, st);
     }
 
     // 1. per-edge messages, written at their target-sorted positions
@@ -681,6 +696,25 @@ extern "C" int ptgnn_b200_gated_forward_fused(int32_t bf16_states, const void *n
                               message_dim, num_types, nullptr, row_ptr, nullptr, nullptr, edge_weights, gru_w_ih, gru_w_hh, gru_b_ih,
                               gru_b_hh, reduce, static_cast<float *>(out_states), workspace, workspace_bytes, weight_cache,
                               weight_cache_bytes, cache_valid, stream, block_plan, num_source_nodes);
+}
+
+extern "C" size_t ptgnn_b200_packed_state_bytes(int64_t num_nodes, int32_t state_dim) {
+    if (num_nodes < 0 || state_dim <= 0) return 0;
+    return fused::packed_state_bytes(3, num_nodes, state_dim);
+}
+extern "C" int ptgnn_b200_gated_forward_fused_chained(const float *node_states, const float *gather_states, const void *packed_states_in,
+                                                      int64_t num_nodes, int64_t num_source_nodes, int32_t state_dim,
+                                                      int32_t message_dim, int32_t num_types, const ptgnn_b200_block_plan *block_plan,
+                                                      const int32_t *row_ptr, const float *const *edge_weights, const float *gru_w_ih,
+                                                      const float *gru_w_hh, const float *gru_b_ih, const float *gru_b_hh,
+                                                      int32_t reduce, float *out_states, void *packed_states_out, void *workspace,
+                                                      size_t workspace_bytes, void *weight_cache, size_t weight_cache_bytes,
+                                                      int32_t cache_valid, void *stream) {
+    PTGNN_CHECK_ARG(block_plan != nullptr, "gated_forward_fused_chained: null block plan");
+    return gated_forward_impl(node_states, gather_states, num_nodes, state_dim, message_dim, num_types, nullptr, row_ptr, nullptr, nullptr,
+                              edge_weights, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, reduce, out_states, workspace, workspace_bytes,
+                              weight_cache, weight_cache_bytes, cache_valid, stream, block_plan, num_source_nodes, packed_states_in,
+                              packed_states_out);
 }
 
 extern "C" size_t ptgnn_b200_mlp_fused_workspace_bytes(int32_t bf16_states, int64_t num_nodes, int64_t num_source_nodes,

@@ -591,7 +591,7 @@ static int gated_forward_bf16_impl(const uint16_t *node_states, const uint16_t *
                 rc = gruws::pack(1, H, D, gru_w_ih, gru_w_hh, gru_b_ih, gru_b_hh, gws, st);
                 if (rc) return rc;
             }
-            return gruws::update(1, agg, h, h, num_nodes, H, D, gws, out_states, st);
+            return gruws::update(1, agg, h, h, num_nodes, H, D, gws, out_states, nullptr, nullptr, st);
         }
     } else {
     // 1. messages

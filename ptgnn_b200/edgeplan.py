@@ -7,6 +7,7 @@ The reference re-derives the same information inside every layer call: it concat
 (``ptgnn_b200_plan_build``: int64->int32, degree histogram, scan, stable radix sort by target) and reused by all
 L layers (the reference's weight-shared stacks call the same layer 7-8 times on the same adjacency).
 """
+import os
 import threading
 from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple
@@ -192,6 +193,45 @@ class shared_plan:
     def __exit__(self, *exc):
         _TLS.plan = self.previous
         return False
+
+
+class state_chain:
+    """`with state_chain() as chain:` -- per-thread hand-off of PACKED node states between consecutive layers of one layer loop.
+    The fp32 fused path computes on fp16 (hi | lo') pairs; a GatedMessagePassingLayer called with `chain.want_output` set also
+    returns that packed form of its output (written by its GRU kernel), and the next layer -- if it is handed the very same tensor
+    object -- skips its packing pass.  Nothing is attached to tensors and nothing outlives the `with` block."""
+
+    def __init__(self):
+        self.want_output = False
+        self._tensor: Optional[torch.Tensor] = None
+        self._packed: Optional[torch.Tensor] = None
+        self._version = None
+        self.previous = None
+
+    def __enter__(self):
+        self.previous = getattr(_TLS, "chain", None)
+        _TLS.chain = self
+        return self
+
+    def __exit__(self, *exc):
+        _TLS.chain = self.previous
+        self._tensor = self._packed = None
+        return False
+
+    def lookup(self, node_states: torch.Tensor) -> Optional[torch.Tensor]:
+        if self._tensor is node_states and self._packed is not None and _version(node_states) == self._version:
+            return self._packed
+        return None
+
+    def store(self, out_states: torch.Tensor, packed: Optional[torch.Tensor]) -> None:
+        self._tensor, self._packed = (out_states, packed) if packed is not None else (None, None)
+        self._version = _version(out_states) if packed is not None else None
+
+
+def current_state_chain() -> Optional[state_chain]:
+    if os.environ.get("PTGNN_B200_CHAIN", "1") == "0":
+        return None
+    return getattr(_TLS, "chain", None)
 
 
 def plan_for(adjacency_lists: Adjacency, num_nodes: int, plan: Optional[EdgePlan] = None,

@@ -11,7 +11,7 @@ from typing import Any, Dict, List, NamedTuple, Optional, Tuple
 import torch
 from torch import nn
 
-from .edgeplan import EdgePlan, clear_plan_cache, plan_for, shared_plan
+from .edgeplan import EdgePlan, clear_plan_cache, plan_for, shared_plan, state_chain
 from .messagepassing import AbstractMessagePassingLayer
 
 
@@ -141,8 +141,11 @@ class GraphNeuralNetwork(nn.Module):
         if node_representations.is_cuda:
             plan = plan_for(adjacency_lists, node_representations.shape[0], plan)
         all_states = [node_representations]
-        with shared_plan(plan):     # per-thread hand-off: the layers of this call (and only they) reuse the plan
-            for layer in self.__message_passing_layers:
+        layers = list(self.__message_passing_layers)
+        # per-thread hand-offs: the layers of this call (and only they) reuse the plan, and pass their packed states on
+        with shared_plan(plan), state_chain() as chain:
+            for i, layer in enumerate(layers):
+                chain.want_output = i + 1 < len(layers)
                 node_representations = layer(
                     node_states=node_representations,
                     adjacency_lists=adjacency_lists,

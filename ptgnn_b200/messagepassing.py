@@ -24,7 +24,7 @@ import ctypes
 import os
 
 from . import _native as N
-from .edgeplan import EdgePlan, current_shared_plan, plan_for
+from .edgeplan import EdgePlan, current_shared_plan, current_state_chain, plan_for
 
 _ACTIVATION_CODES = {type(None): N.ACT_NONE, nn.GELU: N.ACT_GELU, nn.Tanh: N.ACT_TANH, nn.ReLU: N.ACT_RELU}
 
@@ -232,14 +232,30 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
             out = torch.empty_like(h)
             bp = plan.block_plan()
+            # inside a container's layer loop (fp32 states): take the packed form of the input from the previous layer, hand the
+            # packed form of the output to the next one (edgeplan.state_chain) -- one packing pass per stack instead of one per layer
+            chain = None if bf16 else current_state_chain()
+            packed_in = chain.lookup(node_states) if (chain is not None and h is node_states) else None
+            packed_out = None
+            if chain is not None and chain.want_output:
+                packed_out = torch.empty(max(lib.ptgnn_b200_packed_state_bytes(num_nodes, H), 1), dtype=torch.uint8, device=h.device)
             with torch.cuda.device(h.device):
-                rc = lib.ptgnn_b200_gated_forward_fused(
-                    int(bf16), N.ptr(h), N.ptr(gsrc), num_nodes, ns, H, D, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
-                    N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce, N.ptr(out), N.ptr(ws), ws_bytes,
-                    N.ptr(cache), 0 if cache is None else cache.numel(), int(valid), N.current_stream(h.device),
-                )
+                if packed_in is not None or packed_out is not None:
+                    rc = lib.ptgnn_b200_gated_forward_fused_chained(
+                        N.ptr(h), N.ptr(gsrc), N.ptr(packed_in), num_nodes, ns, H, D, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
+                        N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce, N.ptr(out), N.ptr(packed_out),
+                        N.ptr(ws), ws_bytes, N.ptr(cache), 0 if cache is None else cache.numel(), int(valid), N.current_stream(h.device),
+                    )
+                else:
+                    rc = lib.ptgnn_b200_gated_forward_fused(
+                        int(bf16), N.ptr(h), N.ptr(gsrc), num_nodes, ns, H, D, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
+                        N.ptr_table(weights), N.ptr(w_ih), N.ptr(w_hh), N.ptr(b_ih), N.ptr(b_hh), reduce, N.ptr(out), N.ptr(ws), ws_bytes,
+                        N.ptr(cache), 0 if cache is None else cache.numel(), int(valid), N.current_stream(h.device),
+                    )
             N.check(rc, "ptgnn_b200_gated_forward_fused")
             self._weight_cache_filled(kind, h.device)
+            if chain is not None:
+                chain.store(out, packed_out)
             return out
         if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
             cache, valid = self._weight_cache("bf16", lib.ptgnn_b200_gated_weight_cache_bytes_bf16(plan.num_types, H, D), params, h.device)

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    if os.environ.get("PTGNN_TOOLS_LIB"):      # kernel experiments: run the parity tests against another build of the library (tools/)
+        from ptgnn_b200 import _native
+
+        _native.LIB_PATH = os.path.join(ROOT, os.environ["PTGNN_TOOLS_LIB"])
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 

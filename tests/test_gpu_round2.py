@@ -264,3 +264,59 @@ def test_captured_layer_loop_matches_eager_and_follows_its_buffers(dtype):
     with torch.no_grad():
         eager2 = gnn.gnn(h2, gnn.expand_adjacency(raw2, n, "cuda"), None, None, {}, {})
     assert torch.equal(out2, eager2)
+
+
+# ---- 9. packed states handed from layer to layer (edgeplan.state_chain) ------------------------------------------------------------
+def test_state_chain_is_bit_identical_and_skips_the_packing_passes(monkeypatch):
+    """Inside a container's layer loop the GRU kernel of layer i also writes the fp16 (hi | lo') form of its output and layer i + 1
+    skips its packing pass: results bit-identical to the unchained run, L - 1 fewer launches; a tensor that is not the previous
+    layer's output (here: a residual sum) falls back to packing; a stand-alone layer call never chains."""
+    import ptgnn_b200 as P
+    from ptgnn_b200 import _native as N
+    from helpers import random_adjacency
+
+    gen = torch.Generator().manual_seed(5)
+    torch.manual_seed(5)
+    n, counts, L = 5000, [9000, 4000, 0, 700], 4
+    adj = _dev(random_adjacency(gen, n, counts))
+    layers = [P.GatedMessagePassingLayer(128, 128, len(counts), "sum") for _ in range(L)]
+    gnn = P.GraphNeuralNetwork(layers, _Embed(), False, False).cuda().eval()
+    h = torch.randn(n, 128, generator=gen).cuda()
+    with torch.no_grad():
+        gnn.gnn(h, adj, None, None, {}, {})                      # plan + weight caches
+        l0 = N.launch_count()
+        chained = gnn.gnn(h, adj, None, None, {}, {})
+        l1 = N.launch_count()
+        monkeypatch.setenv("PTGNN_B200_CHAIN", "0")
+        plain = gnn.gnn(h, adj, None, None, {}, {})
+        l2 = N.launch_count()
+        monkeypatch.delenv("PTGNN_B200_CHAIN")
+        assert torch.equal(chained, plain)
+        assert (l2 - l1) - (l1 - l0) == L - 1, f"chained {l1 - l0} launches, unchained {l2 - l1}"
+        # every layer's own output is the same with and without the hand-off (all states)
+        a = gnn.gnn(h, adj, None, None, {}, {}, return_all_states=True)
+        monkeypatch.setenv("PTGNN_B200_CHAIN", "0")
+        b = gnn.gnn(h, adj, None, None, {}, {}, return_all_states=True)
+        monkeypatch.delenv("PTGNN_B200_CHAIN")
+        assert torch.equal(a, b)
+        # a layer that gets a different tensor than the previous layer's output must not use the stale packed copy
+        join = P.MeanResidualLayer(128)
+        res = P.GraphNeuralNetwork([join.pass_through_dummy_layer(), layers[0], join, layers[1]], _Embed(), False, False).cuda().eval()
+        got = res.gnn(h, adj, None, None, {}, {})
+        h1 = layers[0](h, adj)
+        want = layers[1](torch.stack((h, h1), dim=-1).mean(dim=-1), adj)
+        assert torch.equal(got, want)
+        # ... and an in-place edit of the handed-over tensor invalidates the packed copy (version counter)
+        with P.edgeplan.shared_plan(P.plan_for(adj, n)), P.edgeplan.state_chain() as chain:
+            chain.want_output = True
+            mid = layers[0](h, adj)
+            assert chain.lookup(mid) is not None
+            mid.mul_(0.5)
+            assert chain.lookup(mid) is None
+            assert torch.equal(layers[1](mid, adj), layers[1](mid.clone(), adj))
+        # overflow in a chained state is still reported
+        big = h.clone(); big[7, 3] = 1e30
+        plan = P.plan_for(adj, n)
+        with pytest.raises(FloatingPointError):
+            gnn.gnn(big, adj, None, None, {}, {})
+            plan.validate()

@@ -73,12 +73,6 @@ for e in ("epi0", "epi1"):
     print(e, "(per sub-group):")
     stats(e, 20, 21, "wait acc_full")
     stats(e, 21, 22, "drain + combine")
-    stats(e, 21, 25, "  first batch: metadata, split")
-    stats(e, 25, 26, "  first batch: LDTM issue + 20 LDS")
-    stats(e, 26, 27, "  first batch: tcgen05.wait::ld")
-    stats(e, 27, 28, "  first batch: combine chain")
-    stats(e, 28, 29, "  first batch: 16 predicated STS")
-    stats(e, 29, 22, "  remaining batches + release")
     period(e, 22, "sub-groups")
     c23 = sorted(clk for clk, _, t in ev[e] if t == 23)
     c24 = sorted(clk for clk, _, t in ev[e] if t == 24)
