@@ -81,16 +81,18 @@ def edge_messages(plan: EdgePlan, source_rows: torch.Tensor, target_rows: Option
     return out
 
 
-def segment_reduce(messages: torch.Tensor, plan: EdgePlan, reduce_code: int) -> torch.Tensor:
-    """torch_scatter.scatter(messages, targets, dim=0, dim_size=N, reduce) over the plan's target-sorted CSR (messages in edge order)."""
+def segment_reduce(messages: torch.Tensor, plan: EdgePlan, reduce_code: int, return_arg: bool = False):
+    """torch_scatter.scatter(messages, targets, dim=0, dim_size=N, reduce) over the plan's target-sorted CSR (messages in edge order).
+    return_arg (max / min): also the [N, D] int64 edge id of each winning message (E for empty targets, torch_scatter's sentinel)."""
     E, D = messages.shape
     out = torch.empty(plan.num_nodes, D, dtype=torch.float32, device=messages.device)
+    arg = torch.empty(plan.num_nodes, D, dtype=torch.int64, device=messages.device) if return_arg else None
     lib = N.lib()
     with torch.cuda.device(messages.device):
         rc = lib.ptgnn_b200_segment_reduce_f32(N.ptr(messages), N.ptr(plan.row_ptr), N.ptr(plan.perm) if E else None, plan.num_nodes, E, D,
-                                               reduce_code, N.ptr(out), None, N.current_stream(messages.device))
+                                               reduce_code, N.ptr(out), N.ptr(arg), N.current_stream(messages.device))
     N.check(rc, "ptgnn_b200_segment_reduce_f32")
-    return out
+    return (out, arg) if return_arg else out
 
 
 def grucell(inp: torch.Tensor, hidden: torch.Tensor, gru: nn.GRUCell) -> torch.Tensor:

@@ -45,8 +45,9 @@ def _reduce_code(name) -> int:
 def _refuse_autograd(module: nn.Module, node_states: torch.Tensor) -> None:
     if torch.is_grad_enabled() and (node_states.requires_grad or any(p.requires_grad for p in module.parameters())):
         raise NotImplementedError(
-            "ptgnn_b200 layers are forward-only this round (backward = SURVEY.md §8 row f-1): call them under "
-            "torch.no_grad() / torch.inference_mode(), or set requires_grad_(False) on the parameters"
+            "this configuration is forward-only (backward, SURVEY.md §8 row f-1, exists for GatedMessagePassingLayer with fp32 "
+            "states and no edge features): call it under torch.no_grad() / torch.inference_mode(), or set requires_grad_(False) "
+            "on the parameters"
         )
 
 
@@ -197,8 +198,16 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
             raise NotImplementedError("training-mode dropout has no native kernel (forward-only round)")
         if self.__edge_feature_dimension == 0:
             _check_no_edge_features(edge_features)
-        _refuse_autograd(self, node_states)
         reduce = _reduce_code(self.__aggregation_fn)
+        from . import autograd as _ag
+        if _ag.needs_grad(self, node_states):
+            # backward: fp32 states, no edge features, unsharded; the forward below runs unchanged under no_grad
+            if self.__edge_feature_dimension != 0 or gather_states is not None or node_states.dtype != torch.float32:
+                _refuse_autograd(self, node_states)
+            _check_states(node_states, self.__state_dimension, "GatedMessagePassingLayer")
+            gru = self.__state_update
+            return _ag.gated_forward_with_grad(self, node_states, adjacency_lists, self.__aggregation_fn, gru.weight_ih, gru.weight_hh,
+                                               gru.bias_ih, gru.bias_hh, [lin.weight for lin in linears])
         if self.__edge_feature_dimension != 0:
             return self._forward_with_edge_features(node_states, adjacency_lists, edge_features, gather_states, reduce)
 

@@ -78,8 +78,12 @@ def test_reference_checkpoints_load():
 
 def test_unsupported_configurations_fail_loudly():
     adj = [(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64))]
-    with pytest.raises(NotImplementedError):  # autograd
+    with pytest.raises(NotImplementedError):  # autograd: Mlp layers are forward-only
+        P.MlpMessagePassingLayer(32, 32, 32, 1, "sum")(torch.zeros(4, 32), adj)
+    with pytest.raises(N.NativeLibraryError):  # Gated layers have a backward (tests/test_gpu_backward.py) -- on CUDA tensors only
         P.GatedMessagePassingLayer(32, 32, 1, "sum")(torch.zeros(4, 32), adj)
+    with pytest.raises(NotImplementedError):  # ... but not for bf16 states
+        P.GatedMessagePassingLayer(32, 32, 1, "sum")(torch.zeros(4, 32, dtype=torch.bfloat16), adj)
     with torch.no_grad():
         with pytest.raises(NotImplementedError):  # training-mode dropout
             P.GatedMessagePassingLayer(32, 32, 1, "sum", dropout_rate=0.5).train()(torch.zeros(4, 32), adj)
