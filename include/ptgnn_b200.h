@@ -295,6 +295,20 @@ int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *node_states, c
                                  void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side minibatch finalisation -- the graph-structure half of GraphNeuralNetworkModel.extend_minibatch_with /
+ * finalize_minibatch (ptgnn/neuralmodels/gnn/graphneuralnetwork.py:386-493).  The host concatenates the graphs' LOCAL int32
+ * ids (edge sources / targets of one edge type, or reference nodes); item_ptr [G+1] (device, int64) = where each graph's items
+ * start in that concatenation, node_ptr [G+1] (device, int64) = exclusive prefix sum of the graphs' node counts.
+ *   offset_ids:  out[i] = local_ids[i] + node_ptr[g(i)]   replaces `sample_adj_list + nodes_in_mb_so_far` (:419-424, :436) and the
+ *                                                         np.concatenate + torch.tensor(..., int64) of :463-469, :485-491
+ *   segment_ids: out[i] = g(i)                            replaces __create_node_to_graph_idx (:441-443, one Python iteration per
+ *                                                         node) with item_ptr = node_ptr, and the extend() of :431-434
+ * ---------------------------------------------------------------------------------------------- */
+int ptgnn_b200_offset_ids(const int32_t *local_ids, int64_t num_items, const int64_t *item_ptr, const int64_t *node_ptr,
+                          int32_t num_graphs, int64_t *out, void *stream);
+int ptgnn_b200_segment_ids(const int64_t *item_ptr, int32_t num_segments, int64_t num_items, int64_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stand-alone pieces of the layers, for the configurations the fused entry points do not cover.
  *   linear:        out[rows, out_dim] = act(x W^T + b)  -- one `nn.Linear` (+ activation) of `MLP.forward` (mlp.py:79-80) or of an
  *                  Mlp layer's dense update (mlpmessagepassing.py:116); fp32-exact on the tensor cores when the dims fit.

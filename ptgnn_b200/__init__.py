@@ -6,6 +6,7 @@ own ``nn.Module`` API.  The arithmetic lives in ``libptgnn_b200.so`` (C ABI: ``i
 is the host-side mirror of the reference interface.  There is no CPU / PyTorch fallback.
 """
 from .aggregation import PnaMessageAggregation
+from .batching import MinibatchAssembler
 from .edgeplan import EdgePlan, clear_plan_cache, plan_for
 from .gnn import GnnOutput, GraphNeuralNetwork
 from .messagepassing import (
@@ -21,6 +22,6 @@ from .scatter import scatter, scatter_add, scatter_max, scatter_mean, scatter_mi
 __all__ = [
     "EdgePlan", "plan_for", "clear_plan_cache", "GnnOutput", "GraphNeuralNetwork", "MLP", "AbstractMessageAggregation",
     "PnaMessageAggregation", "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "MeanResidualLayer",
-    "ConcatResidualLayer", "LinearResidualLayer", "scatter", "scatter_add",
+    "ConcatResidualLayer", "LinearResidualLayer", "MinibatchAssembler", "scatter", "scatter_add",
     "scatter_sum", "scatter_mean", "scatter_max", "scatter_min",
 ]

@@ -179,7 +179,57 @@ def main_round2():
          **{"last::" + k: v.numpy() for k, v in last.state_dict().items()})
 
 
+def main_minibatch():
+    """Runs the UNMODIFIED GraphNeuralNetworkModel.initialize_minibatch / extend_minibatch_with / finalize_minibatch
+    (graphneuralnetwork.py:372-493) on synthetic graphs.  The methods are called on a stand-in `self` that carries exactly the
+    attributes they read (stub node embedder, no edge embedder): the model's constructor needs embedder models and metadata that are
+    out of this path's scope, the three methods do not."""
+    import types
+
+    from ptgnn.neuralmodels.gnn.graphneuralnetwork import GraphNeuralNetworkModel
+    from ptgnn.neuralmodels.gnn.structs import TensorizedGraphData
+
+    class _NodeEmbedderStub:
+        def initialize_minibatch(self):
+            return {}
+
+        def extend_minibatch_with(self, item, mb):
+            return True
+
+        def finalize_minibatch(self, mb, device):
+            return {}
+
+    num_types = 4
+    stub = types.SimpleNamespace(stop_extending_minibatch_after_num_nodes=10 ** 9)
+    setattr(stub, "_GraphNeuralNetworkModel__node_embedding_model", _NodeEmbedderStub())
+    setattr(stub, "_GraphNeuralNetworkModel__edge_embedding_model", None)
+    setattr(stub, "_GraphNeuralNetworkModel__edge_types", {f"e{t}": t for t in range(num_types)})
+    setattr(stub, "_GraphNeuralNetworkModel__create_node_to_graph_idx",
+            getattr(GraphNeuralNetworkModel, "_GraphNeuralNetworkModel__create_node_to_graph_idx"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import minibatch_graphs
+
+    graphs = minibatch_graphs(num_types=num_types)
+    mb = GraphNeuralNetworkModel.initialize_minibatch(stub)
+    for adj, refs, n in graphs:
+        GraphNeuralNetworkModel.extend_minibatch_with(
+            stub, TensorizedGraphData(adjacency_lists=adj, node_tensorized_data=[], edge_features=None, reference_nodes=refs, num_nodes=n), mb)
+    out = GraphNeuralNetworkModel.finalize_minibatch(stub, mb, "cpu")
+    arrays = {"num_graphs": out["num_graphs"], "node_to_graph_idx": out["node_to_graph_idx"].numpy()}
+    for t, (s, g) in enumerate(out["adjacency_lists"]):
+        arrays[f"src{t}"], arrays[f"tgt{t}"] = s.numpy(), g.numpy()
+    for k, v in out["reference_node_ids"].items():
+        arrays[f"ref_ids::{k}"] = v.numpy()
+    for k, v in out["reference_node_graph_idx"].items():
+        arrays[f"ref_graph::{k}"] = v.numpy()
+    save("minibatch", **arrays)
+
+
 if __name__ == "__main__":
+    if "--minibatch-only" in sys.argv:
+        main_minibatch()
+        sys.exit(0)
     if "--round2-only" not in sys.argv:
         main()
     main_round2()
+    main_minibatch()

@@ -89,3 +89,21 @@ def mlp_oracle_call_kwargs(name: str, sd) -> dict:
         dense_activation="tanh",
     )
     return args
+
+
+def minibatch_graphs(seed=21, num_graphs=9, num_types=4):
+    """Per-graph LOCAL structure as GraphNeuralNetworkModel.tensorize produces it (graphneuralnetwork.py:313-322, :350-363): int32
+    arrays, some edge types empty, reference nodes under two names (one of them absent from some graphs)."""
+    rng = np.random.RandomState(seed)
+    graphs = []
+    for g in range(num_graphs):
+        n = int(rng.randint(1, 60))
+        adj = []
+        for t in range(num_types):
+            e = 0 if (t == 2 and g % 3 == 0) else int(rng.randint(0, 4 * n))
+            adj.append((rng.randint(0, n, e).astype(np.int32), rng.randint(0, n, e).astype(np.int32)))
+        refs = {"token-sequence": rng.randint(0, n, int(rng.randint(0, 7))).astype(np.int32)}
+        if g % 2 == 0:
+            refs["candidate_nodes"] = rng.randint(0, n, int(rng.randint(1, 4))).astype(np.int32)
+        graphs.append((adj, refs, n))
+    return graphs

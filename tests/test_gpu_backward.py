@@ -28,6 +28,25 @@ def test_gated_backward_vs_oracle_autograd(agg, n, counts, H):
     adj = random_adjacency(gen, n, counts)
     layer = P.GatedMessagePassingLayer(H, H, len(counts), agg)
     h0 = torch.randn(n, H, generator=gen)
+    if agg in ("max", "min"):
+        # Which edge wins a (target, feature) is decided on messages that carry ~1e-6 of rounding error in the kernels: two
+        # candidates within that distance may legitimately swap, which moves one gradient element between two source rows.
+        # Draw states without such near-ties (the first draw of this seed has one: 1.0542319 vs 1.0542320).
+        for _ in range(8):
+            with torch.no_grad():
+                msgs = torch.cat([torch.nn.functional.linear(h0[s], lin.weight) for (s, _t), lin in
+                                  zip(adj, [m for m in layer.modules() if isinstance(m, torch.nn.Linear)])])
+                tgt = torch.cat([t for _s, t in adj])
+                sign = 1.0 if agg == "max" else -1.0
+                top = O.scatter(sign * msgs, tgt, n, "max")
+                masked = torch.where(sign * msgs >= top[tgt] - 0, torch.full_like(msgs, -3e38), sign * msgs)
+                second = O.scatter(masked, tgt, n, "max")
+                gap = torch.where(second < -1e38, torch.full_like(top, 1.0), top - second)
+            if float(gap.min()) > 2e-5:
+                break
+            h0 = torch.randn(n, H, generator=gen)
+        else:
+            pytest.fail("could not draw states without near-ties")
     probe = torch.randn(n, H, generator=gen)                     # loss = <out, probe>: a generic upstream gradient
 
     # oracle: the same arithmetic as the reference layer, autograd on the CPU
@@ -86,7 +105,7 @@ def test_training_steps_through_the_container():
         loss = ((oracle_forward(ref_params) - target) ** 2).mean()
         loss.backward()
         opt_ref.step()
-        ref_losses.append(float(loss))
+        ref_losses.append(float(loss.detach()))
 
     gnn = gnn.cuda().train()
     adj_d = [(s.cuda(), t.cuda()) for s, t in adj]
@@ -98,7 +117,7 @@ def test_training_steps_through_the_container():
         loss = ((out - target.cuda()) ** 2).mean()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[1] < losses[0]
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (losses, ref_losses)
