@@ -52,6 +52,19 @@ def measured_tensor_peak():
     return 1590.0, "fallback 1.59 PFLOP/s burst (B200_PROFILING.md)"
 
 
+def tcgen05_peaks():
+    """This repo's own tensor-pipe ceiling: back-to-back tcgen05.mma issue rate (csrc/tc_peak.cu, tools/tc_peak.py; committed as
+    profiles/r02_tcgen05_peaks.json).  {"f16": TFLOP/s, "tf32": TFLOP/s} at N = 256 with the A operand in tensor memory, or {}."""
+    path = os.path.join(ROOT, "profiles", "r02_tcgen05_peaks.json")
+    try:
+        with open(path) as f:
+            res = json.load(f)["results"]
+        pick = lambda kind: max(r["tflops"] for r in res if r["kind"] == kind and r["N"] == 256)  # noqa: E731
+        return {"f16": pick("f16"), "tf32": pick("tf32"), "source": "profiles/r02_tcgen05_peaks.json (own tcgen05.mma issue-rate kernel, M=128 N=256)"}
+    except (OSError, ValueError, KeyError):
+        return {}
+
+
 def ncu_traffic(dtype: str):
     """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the CURRENT kernels, from the committed ncu
     --set full capture: profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic from the .ncu-rep of the round.
@@ -196,11 +209,14 @@ def make_batch(workload: str, seed_offset: int = 0, num_graphs=None):
     raise ValueError(workload)
 
 
-def build_model(num_types: int, agg: str):
+def build_model(num_types: int, agg: str, kind: str = "gated"):
     import ptgnn_b200 as P
 
     torch.manual_seed(0)
-    layers = [P.GatedMessagePassingLayer(HIDDEN, HIDDEN, num_types, agg) for _ in range(NUM_LAYERS)]
+    if kind == "mlp":     # the reference's VarMisuse default stack (varmisuse/train.py:43-74) without its residual pseudo-layers
+        layers = [P.MlpMessagePassingLayer(HIDDEN, HIDDEN, HIDDEN, num_types, agg) for _ in range(NUM_LAYERS)]
+    else:
+        layers = [P.GatedMessagePassingLayer(HIDDEN, HIDDEN, num_types, agg) for _ in range(NUM_LAYERS)]
     gnn = P.GraphNeuralNetwork(layers, torch.nn.Identity(), introduce_backwards_edges=True, add_self_edges=True)
     return gnn.eval()
 
@@ -286,6 +302,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agg", default="sum", choices=["sum", "max", "mean", "min"])
     ap.add_argument("--workload", default="graph2class", choices=["graph2class", "varmisuse"])
+    ap.add_argument("--layers", default="gated", choices=["gated", "mlp"],
+                    help="mlp = MlpMessagePassingLayer stack (the VarMisuse default); extra record, not the headline config")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="node-state dtype; f32 is the headline (reference CPU path precision), bf16 = BASELINE.json configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,6 +312,8 @@ def main():
     ap.add_argument("--profile", action="store_true", help="only the HBM-resident loop (for runs under ncu); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.layers == "mlp":
+        args.no_cpu_baseline = True      # the CPU-port leg is written for the headline (gated) stack
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -301,10 +321,10 @@ def main():
     metric = "edges/sec per GNN layer"
     config = {
         "workload": f"{args.workload} synthetic batch per GPU: 80x2560=204,800 nodes, 8 raw edge types -> T=17, E=1,105,920 "
-                    f"layer-level edges, hidden {HIDDEN}, {NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), {args.dtype}"
+                    f"layer-level edges, hidden {HIDDEN}, {NUM_LAYERS} {'Mlp' if args.layers == 'mlp' else 'Gated'}MessagePassingLayers ({args.agg}), {args.dtype}"
                     if args.workload == "graph2class" else
                     f"varmisuse synthetic batch per GPU: 40x2000 nodes, 11 raw types -> T=23, E=480,000, hidden {HIDDEN}, "
-                    f"{NUM_LAYERS} GatedMessagePassingLayers ({args.agg}), {args.dtype}",
+                    f"{NUM_LAYERS} {'Mlp' if args.layers == 'mlp' else 'Gated'}MessagePassingLayers ({args.agg}), {args.dtype}",
         "step": "edge-plan build + 8 layers on one minibatch",
         "parallelism": f"graph-sharded x{world} (no data-path collective)",
         "l2": "per-layer working set (states in + packed copy + aggregate + states out: 0.42 GB fp32 / 0.16 GB bf16) > 126 MB L2 and "
@@ -316,7 +336,7 @@ def main():
         if rank != 0:
             return
         batch = make_batch(args.workload)
-        gnn = build_model(2 * len(batch.adjacency_lists) + 1, args.agg)
+        gnn = build_model(2 * len(batch.adjacency_lists) + 1, args.agg, args.layers)
         r = cpu_reference_run(batch, gnn, args.agg, args.steps, args.warmup, budget_s=150.0)
         line = {
             "impl": "reference", "metric": metric, "value": r["value"], "unit": "edges/s", "n_gpus": args.gpus,
@@ -343,7 +363,7 @@ def main():
 
     batch = make_batch(args.workload, seed_offset=rank)  # every rank owns different graphs (weak scaling)
     T = 2 * len(batch.adjacency_lists) + 1
-    gnn = build_model(T, args.agg).to(dev)
+    gnn = build_model(T, args.agg, args.layers).to(dev)
     E = batch.layer_level_edges()
     n_nodes = batch.num_nodes
 
@@ -527,16 +547,19 @@ def main():
             "reduce": E * D * esz + (n_nodes + 1) * 4 + n_nodes * D * esz,
             "gru": n_nodes * D * esz + 2 * n_nodes * HIDDEN * esz + 6 * HIDDEN * HIDDEN * esz,
         }
+    k_in = 2 * HIDDEN if args.layers == "mlp" else HIDDEN      # Mlp layers: [h_src ; h_tgt] -> message
     alg_flops = {  # the reference's multiply-adds (x2)
-        "message": 2 * E * HIDDEN * D,
+        "message": 2 * E * k_in * D,
         "gru": 2 * n_nodes * (3 * HIDDEN * D + 3 * HIDDEN * HIDDEN),
     }
     # MMAs issued per reference product and their rate relative to the bf16 peak: fused fp32 = 3 kind::f16 products (3xFP16);
     # unfused fp32 message / GRU = 3 kind::tf32 products at half the bf16 rate (3xTF32); bf16 = 1
+    gru_ws = fused and os.environ.get("PTGNN_B200_GRU", "") != "tc"        # weights-stationary GRU kernel: 3xFP16 as well
     if args.dtype == "f32":
-        exact_div = {"message": 3.0 if fused else 6.0, "gru": 6.0}
+        exact_div = {"message": 3.0 if fused else 6.0, "gru": 3.0 if gru_ws else 6.0}
     else:
         exact_div = {"message": 1.0, "gru": 1.0}
+    own_peaks = tcgen05_peaks()
     kernel_names = {"message": "tc_pipeline_kernel<MsgPolicy> (edge messages)", "reduce": "segment_reduce_stream_kernel",
                     "gru": "tc_pipeline_kernel<GruPolicy> (GRUCell update)", "plan": "edge-plan kernels", "pack": "weight split/pack"}
     if args.dtype == "bf16":
@@ -544,6 +567,7 @@ def main():
                             gru="tc_pipeline_bf16_kernel<GruPolicyB>")
     if fused:
         kernel_names.update(message="fused_aggregate_kernel (gather -> W_t -> segmented reduce, %s)" % ("3xFP16" if args.dtype == "f32" else "bf16"),
+                            gru="gru_ws_kernel (weights-stationary GRUCell, %s)" % ("3xFP16" if args.dtype == "f32" else "bf16") if gru_ws else kernel_names["gru"],
                             pack="pack_states_kernel (fp32 -> fp16 hi|lo' rows) + weight packing", plan="edge-plan + block-plan kernels")
     traffic, traffic_src = ncu_traffic(args.dtype)
     kernels = {}
@@ -574,6 +598,8 @@ def main():
         if name in alg_flops:
             entry["tensor_ceiling_tflops"] = ceiling
             entry["frac_tensor_exact_peak"] = entry["alg_tflops"] / ceiling
+            if own_peaks:      # the stricter denominator: this GPU's tcgen05 issue rate (kind::f16; kind::tf32 runs at half of it)
+                entry["frac_of_tcgen05_issue_rate"] = entry["alg_tflops"] / (own_peaks["f16"] / exact_div.get(name, 1.0))
     # the kernel with the largest share of the step
     dominant = max((k for k in kernels if "alg_bytes" in kernels[k] and k != "pack"),
                    key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
@@ -586,6 +612,9 @@ def main():
             "note": "dominant kernel by time. achieved = the reference's multiply-adds (x2) per launch / CUDA-event launch time; "
                     "kernels[*].floor_ms has both floors and kernels[*].frac_hbm the bandwidth view.",
         }
+        if own_peaks:
+            roofline["tcgen05_issue_rate"] = {"f16_tflops": own_peaks["f16"], "tf32_tflops": own_peaks["tf32"], "source": own_peaks["source"],
+                                              "frac": dk.get("frac_of_tcgen05_issue_rate")}
     else:
         roofline = {
             "kernel": dk["kernel"], "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -1,18 +1,24 @@
 #!/bin/bash
-# one GPU session: tests, bench lines, launch list, one full ncu capture of the fused kernel
+# one GPU session: tests, smoke, bench lines (+ reference arm, Mlp-max VarMisuse workload), launch list, full ncu captures of the dominant kernels
+T=${1:-r02f}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_round2.py::test_two_devices_in_one_process 2>&1 | tail -60 > gpurun_out/r02e_tests.txt
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r02e_bench_f32.json 2> gpurun_out/r02e_bench_f32.err
-timeout 300 python bench.py --steps 20 --warmup 5 --dtype bf16 > gpurun_out/r02e_bench_bf16.json 2> gpurun_out/r02e_bench_bf16.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/r02e_launches.csv python bench.py --profile --steps 2 --warmup 3 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_aggregate -s 10 -c 2 -o gpurun_out/r02e_fused_f32 python bench.py --profile --steps 2 --warmup 3 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_aggregate -s 10 -c 2 -o gpurun_out/r02e_fused_bf16 python bench.py --profile --steps 2 --warmup 3 --dtype bf16 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:^gru_ws -s 10 -c 1 -o gpurun_out/r02e_gru_f32 python bench.py --profile --steps 2 --warmup 3 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:^gru_ws -s 10 -c 1 -o gpurun_out/r02e_gru_bf16 python bench.py --profile --steps 2 --warmup 3 --dtype bf16 > /dev/null 2>&1
-cat gpurun_out/r02e_tests.txt | tail -15
-python - <<'PY'
+timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_round2.py::test_two_devices_in_one_process 2>&1 | tail -60 > gpurun_out/${T}_tests.txt
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_f32.json 2> gpurun_out/${T}_bench_f32.err
+timeout 300 python bench.py --steps 20 --warmup 5 --dtype bf16 > gpurun_out/${T}_bench_bf16.json 2> gpurun_out/${T}_bench_bf16.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
+timeout 300 python bench.py --steps 20 --warmup 5 --workload varmisuse --agg max --layers mlp > gpurun_out/${T}_bench_varmisuse_max.json 2> gpurun_out/${T}_bench_varmisuse_max.err
+timeout 200 python __graft_entry__.py --smoke > gpurun_out/${T}_smoke.txt 2>&1
+PTGNN_FUSED_TRACE=1 python tools/fused_trace.py f32 > gpurun_out/${T}_trace_f32.txt 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --profile --steps 2 --warmup 3 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_aggregate -s 10 -c 2 -o gpurun_out/${T}_fused_f32 python bench.py --profile --steps 2 --warmup 3 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_aggregate -s 10 -c 2 -o gpurun_out/${T}_fused_bf16 python bench.py --profile --steps 2 --warmup 3 --dtype bf16 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:^gru_ws -s 10 -c 1 -o gpurun_out/${T}_gru_f32 python bench.py --profile --steps 2 --warmup 3 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:^gru_ws -s 10 -c 1 -o gpurun_out/${T}_gru_bf16 python bench.py --profile --steps 2 --warmup 3 --dtype bf16 > /dev/null 2>&1
+cat gpurun_out/${T}_tests.txt | tail -15
+tail -3 gpurun_out/${T}_smoke.txt
+python - <<PY
 import json
-for f in ("gpurun_out/r02e_bench_f32.json", "gpurun_out/r02e_bench_bf16.json"):
+for f in ("gpurun_out/${T}_bench_f32.json", "gpurun_out/${T}_bench_bf16.json"):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, "ms/step", round(d["ms_per_step"], 3), "value", "%.3e" % d["value"], "e2e", "%.3e" % d["e2e"]["value"], "serial ms", round(d["e2e"]["serial_ms_per_step"], 2),
