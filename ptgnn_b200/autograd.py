@@ -13,12 +13,19 @@ edge-sized work on the native kernels:
 * parameter gradients (``dW_t``, ``dW_ih``, ``dW_hh``): plain ``[out, rows] x [rows, in]`` GEMMs with a huge K (rows = edges or
   nodes) -- library GEMMs (``torch.matmul`` = cuBLAS), as are the bias column sums.
 
-fp32 states only; training-mode dropout (a per-edge mask on the gathered rows, gatedmessagepassing.py:59) and edge features
-still raise.  Parity: ``tests/test_gpu_backward.py`` against ``torch.autograd`` through the CPU oracle (1e-4).
+``MlpMessagePassingLayer`` (default message MLP) follows the same scheme; its node-sized tail (activation, LayerNorm, dense layer:
+mlpmessagepassing.py:114-117) is differentiated by a local ``torch.autograd.grad`` over library ops, and its output Dropout is a torch
+op applied outside the Function.
+
+The gated layer's training-mode dropout (a per-edge mask on the gathered rows, gatedmessagepassing.py:59) and edge features under
+autograd need the gathered ``[E_t, H]`` rows to exist: they run as the reference writes the layer, with the Linear / scatter / GRUCell
+as differentiable native operators (``gated_forward_composed``).  fp32 states only.  Parity: ``tests/test_gpu_backward.py`` against ``torch.autograd`` through the CPU oracle (1e-4).
 """
-from typing import List, Tuple
+import threading
+from typing import List, Optional, Tuple
 
 import torch
+import torch.nn.functional as F_
 
 from . import _native as N
 from . import composed as C
@@ -26,8 +33,49 @@ from .edgeplan import plan_for
 from .scatter import scatter_sum
 
 
+_TLS = threading.local()
+
+
+class _suppress_output_dropout:
+    """Inside an autograd.Function's forward the layer is re-entered under no_grad: its output dropout is applied OUTSIDE the
+    Function (a differentiable torch op on the Function's result), not in the inner call."""
+
+    def __enter__(self):
+        self.previous = getattr(_TLS, "suppress", False)
+        _TLS.suppress = True
+
+    def __exit__(self, *exc):
+        _TLS.suppress = self.previous
+        return False
+
+
+def output_dropout_suppressed() -> bool:
+    return getattr(_TLS, "suppress", False)
+
+
 def needs_grad(module: torch.nn.Module, node_states: torch.Tensor) -> bool:
     return torch.is_grad_enabled() and (node_states.requires_grad or any(p.requires_grad for p in module.parameters()))
+
+
+def _gru_backward(g, agg, h, w_ih, w_hh, b_ih, b_hh):
+    """Gradients of torch.nn.GRUCell (gate order r, z, n) w.r.t. (input, hidden, weight_ih, weight_hh, bias_ih, bias_hh): gate
+    pre-activations and the two input-gradient products on the native dense kernel, gate derivatives pointwise, the parameter
+    gradients ([3H, N] x [N, .], K = num_nodes) as library GEMMs."""
+    gi = C.linear(agg, w_ih, b_ih)
+    gh = C.linear(h, w_hh, b_hh)
+    i_r, i_z, i_n = gi.chunk(3, dim=1)
+    h_r, h_z, h_n = gh.chunk(3, dim=1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    d_n_pre = g * (1.0 - z) * (1.0 - n * n)
+    d_z_pre = g * (h - n) * z * (1.0 - z)
+    d_r_pre = d_n_pre * h_n * r * (1.0 - r)
+    d_gi = torch.cat([d_r_pre, d_z_pre, d_n_pre], dim=1)                 # [N, 3H]
+    d_gh = torch.cat([d_r_pre, d_z_pre, d_n_pre * r], dim=1)
+    d_h = g * z + C.linear(d_gh, w_hh.t().contiguous())                  # direct path + through W_hh
+    d_agg = C.linear(d_gi, w_ih.t().contiguous())                        # [N, D]
+    return d_agg, d_h, d_gi.t() @ agg, d_gh.t() @ h, d_gi.sum(dim=0), d_gh.sum(dim=0)
 
 
 class _GatedLayerFunction(torch.autograd.Function):
@@ -63,24 +111,8 @@ class _GatedLayerFunction(torch.autograd.Function):
             agg = C.segment_reduce(msg, plan, reduce)
         del msg
 
-        # ---- 2. GRUCell backward (gate order r, z, n; torch.nn.GRUCell)
-        gi = C.linear(agg, w_ih, b_ih.detach())
-        gh = C.linear(h, w_hh, b_hh.detach())
-        i_r, i_z, i_n = gi.chunk(3, dim=1)
-        h_r, h_z, h_n = gh.chunk(3, dim=1)
-        r = torch.sigmoid(i_r + h_r)
-        z = torch.sigmoid(i_z + h_z)
-        n = torch.tanh(i_n + r * h_n)
-        d_n_pre = g * (1.0 - z) * (1.0 - n * n)
-        d_z_pre = g * (h - n) * z * (1.0 - z)
-        d_r_pre = d_n_pre * h_n * r * (1.0 - r)
-        d_gi = torch.cat([d_r_pre, d_z_pre, d_n_pre], dim=1)                 # [N, 3H]
-        d_gh = torch.cat([d_r_pre, d_z_pre, d_n_pre * r], dim=1)
-        d_h = g * z + C.linear(d_gh, w_hh.t().contiguous())                  # direct path + through W_hh
-        d_agg = C.linear(d_gi, w_ih.t().contiguous())                        # [N, D]
-        d_w_ih = d_gi.t() @ agg                                              # K = num_nodes: library GEMMs
-        d_w_hh = d_gh.t() @ h
-        d_b_ih, d_b_hh = d_gi.sum(dim=0), d_gh.sum(dim=0)
+        # ---- 2. GRUCell backward
+        d_agg, d_h, d_w_ih, d_w_hh, d_b_ih, d_b_hh = _gru_backward(g, agg, h, w_ih, w_hh, b_ih.detach(), b_hh.detach())
 
         # ---- 3. aggregation + per-type Linear backward
         d_W = []
@@ -115,3 +147,204 @@ class _GatedLayerFunction(torch.autograd.Function):
 
 def gated_forward_with_grad(layer, node_states, adjacency_lists, reduce_name, w_ih, w_hh, b_ih, b_hh, weights):
     return _GatedLayerFunction.apply(layer, adjacency_lists, reduce_name, node_states, w_ih, w_hh, b_ih, b_hh, *weights)
+
+
+# =====================================================================================================================
+# MlpMessagePassingLayer (default message MLP: one bias-free Linear per edge type; string aggregation; no edge features)
+#   out = state_update(message_activation(reduce_{e -> v} W_t [h_src(e) ; h_tgt(e)]))      mlpmessagepassing.py:68-117
+# =====================================================================================================================
+def _node_tail(agg: torch.Tensor, message_activation, ln, dense, dense_activation) -> torch.Tensor:
+    """mlpmessagepassing.py:114-117 without the trailing Dropout: node-sized pointwise ops, LayerNorm and one [N, D] x [D, H] Linear."""
+    x = agg if message_activation is None else message_activation(agg)
+    if ln is not None:
+        x = F_.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps)
+    if dense is not None:
+        x = F_.linear(x, dense.weight, dense.bias)
+        if dense_activation is not None:
+            x = dense_activation(x)
+    return x
+
+
+class _MlpLayerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layer, adjacency_lists, reduce_name, use_target, modules, num_tail_params, h, *params):
+        with torch.no_grad(), _suppress_output_dropout():
+            out = layer(h.detach(), adjacency_lists)
+        ctx.save_for_backward(h, *params)
+        ctx.adjacency_lists, ctx.reduce_name, ctx.use_target = adjacency_lists, reduce_name, use_target
+        ctx.modules, ctx.num_tail_params = modules, num_tail_params
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        h, *params = ctx.saved_tensors
+        tail_params, weights = params[:ctx.num_tail_params], params[ctx.num_tail_params:]
+        adj: List[Tuple[torch.Tensor, torch.Tensor]] = ctx.adjacency_lists
+        reduce_name, use_target = ctx.reduce_name, ctx.use_target
+        message_activation, ln, dense, dense_activation = ctx.modules
+        reduce = N.REDUCE[reduce_name]
+        g = grad_out.contiguous().float()
+        h = h.detach().contiguous()
+        num_nodes, H = h.shape
+        W = [w.detach().contiguous() for w in weights]
+        plan = plan_for(adj, num_nodes)
+        E = plan.num_edges
+
+        # ---- 1. re-compute the aggregate on the native kernels
+        msg = C.edge_messages(plan, h, h if use_target else None, W, use_target)
+        arg = None
+        if reduce_name in ("max", "min"):
+            agg, arg = C.segment_reduce(msg, plan, reduce, return_arg=True)
+        else:
+            agg = C.segment_reduce(msg, plan, reduce)
+        del msg
+
+        # ---- 2. node-sized tail (activation, LayerNorm, dense): local autograd over library ops
+        agg_leaf = agg.detach().requires_grad_(True)
+        with torch.enable_grad():
+            tail = _node_tail(agg_leaf, message_activation, ln, dense, dense_activation)
+            wanted = [agg_leaf] + [p for p in tail_params if p.requires_grad]
+            grads = torch.autograd.grad(tail, wanted, g, allow_unused=True)
+        d_agg = grads[0].contiguous()
+        it = iter(grads[1:])
+        d_tail = [next(it) if p.requires_grad else None for p in tail_params]
+
+        # ---- 3. aggregation + per-type Linear backward
+        d_h = torch.zeros_like(h)
+        d_W = []
+        Ws = [w[:, :H].contiguous() for w in W]                              # columns multiplying h_src
+        Wg = [w[:, H:].contiguous() for w in W] if use_target else None      # columns multiplying h_tgt
+        if reduce_name in ("sum", "mean"):
+            if reduce_name == "mean":
+                cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
+                d_agg = (d_agg / cnt[:, None]).contiguous()
+            for (src, tgt), w in zip(adj, W):
+                if src.numel() == 0:
+                    d_W.append(torch.zeros_like(w))
+                    continue
+                rows = h.index_select(0, src)
+                if use_target:
+                    rows = torch.cat([rows, h.index_select(0, tgt)], dim=1)
+                d_W.append(d_agg.index_select(0, tgt).t() @ rows)
+            if E > 0:
+                rplan = plan_for([(tgt, src) for src, tgt in adj], num_nodes)                     # transposed graph: d h_src
+                back = C.edge_messages(rplan, d_agg, None, [w.t().contiguous() for w in Ws], False)
+                d_h = d_h + C.segment_reduce(back, rplan, N.REDUCE["sum"])
+                if use_target:                                                                     # d h_tgt: every edge sends W_g^T d_agg[v] to its own target v
+                    tplan = plan_for([(tgt, tgt) for _src, tgt in adj], num_nodes)
+                    back = C.edge_messages(tplan, d_agg, None, [w.t().contiguous() for w in Wg], False)
+                    d_h = d_h + C.segment_reduce(back, tplan, N.REDUCE["sum"])
+        else:
+            D = d_agg.shape[1]
+            d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)
+            d_msg.scatter_(0, arg, d_agg)
+            lo = 0
+            for t, ((src, tgt), w) in enumerate(zip(adj, W)):
+                e_t = src.numel()
+                part = d_msg[lo:lo + e_t].contiguous()
+                lo += e_t
+                if e_t == 0:
+                    d_W.append(torch.zeros_like(w))
+                    continue
+                rows = h.index_select(0, src)
+                if use_target:
+                    rows = torch.cat([rows, h.index_select(0, tgt)], dim=1)
+                d_W.append(part.t() @ rows)
+                d_h = d_h + scatter_sum(C.linear(part, Ws[t].t().contiguous()), src, dim=0, dim_size=num_nodes)
+                if use_target:
+                    d_h = d_h + scatter_sum(C.linear(part, Wg[t].t().contiguous()), tgt, dim=0, dim_size=num_nodes)
+        return (None, None, None, None, None, None, d_h, *d_tail, *d_W)
+
+
+def mlp_forward_with_grad(layer, node_states, adjacency_lists, reduce_name, use_target, message_activation, ln, dense, dense_activation,
+                          weights):
+    tail_params: List[Optional[torch.Tensor]] = []
+    if ln is not None:
+        tail_params += [ln.weight, ln.bias]
+    if dense is not None:
+        tail_params += [dense.weight] + ([dense.bias] if dense.bias is not None else [])
+    return _MlpLayerFunction.apply(layer, adjacency_lists, reduce_name, bool(use_target), (message_activation, ln, dense, dense_activation),
+                                   len(tail_params), node_states, *tail_params, *weights)
+
+
+# =====================================================================================================================
+# Differentiable stand-alone operators: the composed path (edge features, per-edge dropout) under autograd
+# =====================================================================================================================
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) on the native dense kernel; dx on the same kernel, dW / db as library GEMM / column sum."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return C.linear(x.detach().contiguous(), weight.detach().contiguous(), None if bias is None else bias.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        return C.linear(g, weight.detach().t().contiguous()), g.t() @ x.detach(), (g.sum(dim=0) if ctx.has_bias else None)
+
+
+class _SegmentReduceFn(torch.autograd.Function):
+    """torch_scatter.scatter(messages, targets, reduce) on the native segmented-reduce kernel; backward = gather of the target's
+    gradient (sum / mean) or routing to the winning edge (max / min, torch_scatter's arg semantics)."""
+
+    @staticmethod
+    def forward(ctx, messages, plan, reduce_name):
+        ctx.plan, ctx.reduce_name = plan, reduce_name
+        m = messages.detach().contiguous()
+        if reduce_name in ("max", "min"):
+            out, arg = C.segment_reduce(m, plan, N.REDUCE[reduce_name], return_arg=True)
+            ctx.save_for_backward(arg)
+            return out
+        return C.segment_reduce(m, plan, N.REDUCE[reduce_name])
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, reduce_name = ctx.plan, ctx.reduce_name
+        g = g.contiguous()
+        E = plan.num_edges
+        if reduce_name in ("max", "min"):
+            (arg,) = ctx.saved_tensors
+            d_msg = torch.zeros(E + 1, g.shape[1], dtype=g.dtype, device=g.device)
+            d_msg.scatter_(0, arg, g)
+            return d_msg[:E], None, None
+        if reduce_name == "mean":
+            cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(g.dtype)
+            g = g / cnt[:, None]
+        return g.index_select(0, plan.tgt32.long()), None, None
+
+
+class _GRUCellFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, agg, h, w_ih, w_hh, b_ih, b_hh):
+        import types
+
+        ctx.save_for_backward(agg, h, w_ih, w_hh, b_ih, b_hh)
+        shim = types.SimpleNamespace(weight_ih=w_ih.detach(), weight_hh=w_hh.detach(), bias_ih=b_ih.detach(), bias_hh=b_hh.detach())
+        return C.grucell(agg.detach().contiguous(), h.detach().contiguous(), shim)
+
+    @staticmethod
+    def backward(ctx, g):
+        agg, h, w_ih, w_hh, b_ih, b_hh = (t.detach() for t in ctx.saved_tensors)
+        return _gru_backward(g.contiguous(), agg.contiguous(), h.contiguous(), w_ih.contiguous(), w_hh.contiguous(), b_ih, b_hh)
+
+
+def gated_forward_composed(layer_weights, gru, node_states, adjacency_lists, edge_features, reduce_name, dropout_p: float):
+    """GatedMessagePassingLayer.forward exactly as the reference writes it (gatedmessagepassing.py:46-69) -- gather, cat with the edge
+    features, Dropout on the per-edge rows, per-type Linear, scatter, GRUCell -- with the Linear / scatter / GRUCell on the native
+    kernels as differentiable operators.  Used where the [E_t, H] gathered rows must exist: per-edge dropout (training mode) and
+    edge features under autograd."""
+    num_nodes = node_states.shape[0]
+    plan = plan_for(adjacency_lists, num_nodes)
+    msgs = []
+    for t, ((src, _tgt), w) in enumerate(zip(adjacency_lists, layer_weights)):
+        x = F_.embedding(src, node_states)
+        f = None if edge_features is None else edge_features[t]
+        if f is not None and f.dim() == 2 and f.shape[1] > 0:
+            x = torch.cat([x, f.to(x.dtype)], dim=-1)
+        x = F_.dropout(x, dropout_p, dropout_p > 0)
+        msgs.append(_LinearFn.apply(x, w, None))
+    agg = _SegmentReduceFn.apply(torch.cat(msgs, dim=0), plan, reduce_name)
+    return _GRUCellFn.apply(agg, node_states, gru.weight_ih, gru.weight_hh, gru.bias_ih, gru.bias_hh)

@@ -194,15 +194,24 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
     ) -> torch.Tensor:
         linears = self.__edge_message_transformation_layers
         assert len(adjacency_lists) == len(linears), "one adjacency list per edge type is required"
-        if self.training and self.__dropout.p > 0:
-            raise NotImplementedError("training-mode dropout has no native kernel (forward-only round)")
         if self.__edge_feature_dimension == 0:
             _check_no_edge_features(edge_features)
         reduce = _reduce_code(self.__aggregation_fn)
         from . import autograd as _ag
-        if _ag.needs_grad(self, node_states):
-            # backward: fp32 states, no edge features, unsharded; the forward below runs unchanged under no_grad
-            if self.__edge_feature_dimension != 0 or gather_states is not None or node_states.dtype != torch.float32:
+        drop_p = self.__dropout.p if self.training else 0.0
+        grad = _ag.needs_grad(self, node_states)
+        if drop_p > 0 or (grad and self.__edge_feature_dimension != 0):
+            # per-edge dropout (gatedmessagepassing.py:59) / edge features under autograd: the gathered rows have to exist -- the layer
+            # as the reference writes it, Linear / scatter / GRUCell on the native kernels as differentiable operators
+            if gather_states is not None or node_states.dtype != torch.float32:
+                raise NotImplementedError("training-mode dropout / edge features with gradients: fp32 states, unsharded only")
+            _check_states(node_states, self.__state_dimension, "GatedMessagePassingLayer")
+            h = N.require_cuda(node_states, "node_states", torch.float32)
+            return _ag.gated_forward_composed([lin.weight for lin in linears], self.__state_update, h, adjacency_lists,
+                                              edge_features if self.__edge_feature_dimension != 0 else None, self.__aggregation_fn, drop_p)
+        if grad:
+            # backward: fp32 states, unsharded; the forward below runs unchanged under no_grad inside the Function
+            if gather_states is not None or node_states.dtype != torch.float32:
                 _refuse_autograd(self, node_states)
             _check_states(node_states, self.__state_dimension, "GatedMessagePassingLayer")
             gru = self.__state_update
@@ -492,27 +501,43 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
     ) -> torch.Tensor:
         mlps = self.__edge_message_transformation_layers
         assert len(adjacency_lists) == len(mlps), "The number of adjacency lists must be equal to the number of edge types."
-        _refuse_autograd(self, node_states)
-        if (not isinstance(self.__aggregation_fn, str) or self.__features_dim != 0
-                or any(m.num_hidden_layers != 0 or m.uses_biases for m in mlps)):
+        from . import autograd as _ag
+        default_config = (isinstance(self.__aggregation_fn, str) and self.__features_dim == 0
+                          and not any(m.num_hidden_layers != 0 or m.uses_biases for m in mlps))
+        grad = _ag.needs_grad(self, node_states)
+        if grad and (not default_config or gather_states is not None or node_states.dtype != torch.float32):
+            _refuse_autograd(self, node_states)
+        if not default_config:
             return self._forward_composed(node_states, adjacency_lists, edge_features, gather_states)
         _check_no_edge_features(edge_features)
         reduce = _reduce_code(self.__aggregation_fn)
-        msg_act = _activation_code(self.__message_activation, "message_activation")
 
         ln: Optional[nn.LayerNorm] = None
         dense: Optional[nn.Linear] = None
-        dense_act = N.ACT_NONE
+        dense_act_module: Optional[nn.Module] = None
+        drop_p = 0.0
         for m in self.__state_update:
             if isinstance(m, nn.LayerNorm):
                 ln = m
             elif isinstance(m, nn.Linear):
                 dense = m
             elif isinstance(m, nn.Dropout):
-                if self.training and m.p > 0:
-                    raise NotImplementedError("training-mode dropout has no native kernel (forward-only round)")
+                drop_p = m.p if self.training else 0.0
             else:
-                dense_act = _activation_code(m, "dense_activation")
+                dense_act_module = m
+        # the trailing nn.Dropout of the state update (mlpmessagepassing.py:65) acts on the layer's [N, H_out] output: a torch op on the
+        # result (differentiable), never inside the kernels; suppressed when an autograd.Function re-enters the layer
+        if drop_p > 0 and not _ag.output_dropout_suppressed():
+            apply_dropout = lambda t: torch.nn.functional.dropout(t, drop_p, True)  # noqa: E731
+        else:
+            apply_dropout = lambda t: t  # noqa: E731
+        if grad:   # backward: the forward below runs unchanged under no_grad inside the Function
+            _check_states(node_states, self.__input_state_dim, "MlpMessagePassingLayer")
+            return apply_dropout(_ag.mlp_forward_with_grad(
+                self, node_states, adjacency_lists, self.__aggregation_fn, self.__use_target_state_as_message_input,
+                self.__message_activation, ln, dense, dense_act_module, [m.single_linear.weight for m in mlps]))
+        msg_act = _activation_code(self.__message_activation, "message_activation")
+        dense_act = N.ACT_NONE if dense_act_module is None else _activation_code(dense_act_module, "dense_activation")
 
         state_dtype = node_states.dtype if node_states.dtype == torch.bfloat16 else torch.float32
         _check_states(node_states, self.__input_state_dim, "MlpMessagePassingLayer")
@@ -550,7 +575,7 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
                     N.ptr(d_w), N.ptr(d_b), dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
                 )
             N.check(rc, "ptgnn_b200_mlp_forward_fused")
-            return out
+            return apply_dropout(out)
         if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
             ut = int(self.__use_target_state_as_message_input)
             ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes_bf16(num_nodes, plan.num_edges, plan.num_types, H, D, out_dim, ut)
@@ -564,7 +589,7 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
                     N.current_stream(h.device),
                 )
             N.check(rc, "ptgnn_b200_mlp_forward_bf16")
-            return out
+            return apply_dropout(out)
         ws_bytes = lib.ptgnn_b200_mlp_workspace_bytes(
             num_nodes, plan.num_edges, plan.num_types, H, D, out_dim, int(self.__use_target_state_as_message_input))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
@@ -577,7 +602,7 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
                 dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
             )
         N.check(rc, "ptgnn_b200_mlp_forward_f32")
-        return out
+        return apply_dropout(out)
 
     def _forward_composed(self, node_states, adjacency_lists, edge_features, gather_states) -> torch.Tensor:
         """Module aggregators (PNA ...), message MLPs with hidden layers / biases, edge features (mlpmessagepassing.py:82-117 in

@@ -78,14 +78,17 @@ def test_reference_checkpoints_load():
 
 def test_unsupported_configurations_fail_loudly():
     adj = [(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64))]
-    with pytest.raises(NotImplementedError):  # autograd: Mlp layers are forward-only
+    # training (tests/test_gpu_backward.py) exists for both layer classes -- on CUDA tensors only, fp32 only
+    with pytest.raises(N.NativeLibraryError):
         P.MlpMessagePassingLayer(32, 32, 32, 1, "sum")(torch.zeros(4, 32), adj)
-    with pytest.raises(N.NativeLibraryError):  # Gated layers have a backward (tests/test_gpu_backward.py) -- on CUDA tensors only
+    with pytest.raises(N.NativeLibraryError):
         P.GatedMessagePassingLayer(32, 32, 1, "sum")(torch.zeros(4, 32), adj)
-    with pytest.raises(NotImplementedError):  # ... but not for bf16 states
+    with pytest.raises(NotImplementedError):  # ... not for bf16 states
         P.GatedMessagePassingLayer(32, 32, 1, "sum")(torch.zeros(4, 32, dtype=torch.bfloat16), adj)
+    with pytest.raises(NotImplementedError):  # ... nor for message MLPs with hidden layers
+        P.MlpMessagePassingLayer(32, 32, 32, 1, "sum", mlp_hidden_layers=1)(torch.zeros(4, 32), adj)
     with torch.no_grad():
-        with pytest.raises(NotImplementedError):  # training-mode dropout
+        with pytest.raises(N.NativeLibraryError):  # training-mode dropout runs (per-edge mask on the gathered rows) -- on CUDA tensors
             P.GatedMessagePassingLayer(32, 32, 1, "sum", dropout_rate=0.5).train()(torch.zeros(4, 32), adj)
         with pytest.raises(N.NativeLibraryError):  # hidden MLP layers are supported (composed path) -- on CUDA tensors only
             P.MlpMessagePassingLayer(32, 32, 32, 1, "sum", mlp_hidden_layers=1).eval()(torch.zeros(4, 32), adj)
