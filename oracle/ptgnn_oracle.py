@@ -178,6 +178,31 @@ def mlp_layer_forward(
     return agg
 
 
+def egc_layer_forward(
+    node_states: torch.Tensor,
+    adjacency_lists: Adjacency,
+    bases_weights: Sequence[torch.Tensor],
+    coeff_weight: torch.Tensor,
+    coeff_bias: torch.Tensor,
+    aggregation_fn: str,
+    num_heads: int,
+    num_bases: int,
+) -> torch.Tensor:
+    """egcmessagepassing.py:54-91 in eval mode (dropout = identity).  ``bases_weights[t]`` is ``[num_bases * out, H]``."""
+    assert len(adjacency_lists) == len(bases_weights)
+    out_dim = bases_weights[0].shape[0] // num_bases
+    node_weights = F.linear(node_states, coeff_weight, coeff_bias).reshape(-1, num_heads, num_bases, 1)         # :64-66
+    targets, messages = [], []
+    for (src, tgt), w in zip(adjacency_lists, bases_weights):                                                   # :69-83
+        targets.append(tgt)
+        messages.append(F.linear(F.embedding(src, node_states), w).reshape(-1, num_heads, num_bases, out_dim // num_heads))
+    msg = torch.cat(messages, 0)
+    # torch_scatter.scatter on dim 0 of a 4-D tensor (:85-89) == the 2-D scatter on the flattened trailing dimensions
+    agg = aggregate_messages(msg.reshape(msg.shape[0], -1), torch.cat(targets, 0), node_states.shape[0], aggregation_fn)
+    agg = agg.reshape(-1, num_heads, num_bases, out_dim // num_heads)
+    return (agg * node_weights).sum(dim=-2).reshape(-1, out_dim)                                                # :90
+
+
 # --------------------------------------------------------------------------------------------
 # Container bookkeeping
 # --------------------------------------------------------------------------------------------

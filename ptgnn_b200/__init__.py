@@ -8,6 +8,7 @@ is the host-side mirror of the reference interface.  There is no CPU / PyTorch f
 from .aggregation import PnaMessageAggregation
 from .batching import MinibatchAssembler
 from .edgeplan import EdgePlan, clear_plan_cache, plan_for
+from .egc import EGCMessagePassingLayer
 from .gnn import GnnOutput, GraphNeuralNetwork
 from .messagepassing import (
     MLP,
@@ -21,7 +22,7 @@ from .scatter import scatter, scatter_add, scatter_max, scatter_mean, scatter_mi
 
 __all__ = [
     "EdgePlan", "plan_for", "clear_plan_cache", "GnnOutput", "GraphNeuralNetwork", "MLP", "AbstractMessageAggregation",
-    "PnaMessageAggregation", "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "MeanResidualLayer",
+    "PnaMessageAggregation", "AbstractMessagePassingLayer", "GatedMessagePassingLayer", "MlpMessagePassingLayer", "EGCMessagePassingLayer", "MeanResidualLayer",
     "ConcatResidualLayer", "LinearResidualLayer", "MinibatchAssembler", "scatter", "scatter_add",
     "scatter_sum", "scatter_mean", "scatter_max", "scatter_min",
 ]

@@ -225,11 +225,30 @@ def main_minibatch():
     save("minibatch", **arrays)
 
 
+def main_egc():
+    """EGCMessagePassingLayer (egcmessagepassing.py) run unmodified: sum and max, 3 edge types (one empty), H = 64 -> 64."""
+    from ptgnn.neuralmodels.gnn.messagepassing.egcmessagepassing import EGCMessagePassingLayer
+
+    for agg in ("sum", "max"):
+        gen = torch.Generator().manual_seed(31)
+        torch.manual_seed(31)
+        n, counts = 300, [900, 0, 250]
+        adj = random_graph(gen, n, counts)
+        h = torch.randn(n, 64, generator=gen)
+        layer = EGCMessagePassingLayer(64, 64, len(counts), agg, num_bases=4, num_heads=8)
+        out = run_layer(layer, h, adj)
+        save(f"egc_{agg}", h=h.numpy(), out=out.numpy(), **pack("", adj), **state(layer))
+
+
 if __name__ == "__main__":
     if "--minibatch-only" in sys.argv:
         main_minibatch()
+        sys.exit(0)
+    if "--egc-only" in sys.argv:
+        main_egc()
         sys.exit(0)
     if "--round2-only" not in sys.argv:
         main()
     main_round2()
     main_minibatch()
+    main_egc()
