@@ -308,6 +308,7 @@ def main():
                     help="node-state dtype; f32 is the headline (reference CPU path precision), bf16 = BASELINE.json configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="do not measure the CUDA-graph replay variant of the e2e loop")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward + backward extra measurement")
     ap.add_argument("--no-row-shard", action="store_true", help="skip the node-range-split (all-gather) extra measurement")
     ap.add_argument("--profile", action="store_true", help="only the HBM-resident loop (for runs under ncu); prints no bench line")
     args = ap.parse_args()
@@ -662,6 +663,32 @@ def main():
                      "allgather_ms_per_step": ms_ag, "allgather_bytes_per_layer": n_nodes * HIDDEN * esz,
                      "note": "the all-gathers are not overlapped with compute: allgather_ms_per_step is fully exposed"}
 
+    # ---- training step (extra record, kept out of `value`): forward + backward of the same 8-layer stack on
+    # the same resident minibatch, loss = mean of the output states, gradients for the states and every parameter
+    train = None
+    if args.dtype == "f32" and world == 1 and not args.no_train:
+        try:
+            gnn.train()
+            h_train = h_dev.clone().requires_grad_(True)
+
+            def step_train():
+                P.clear_plan_cache()
+                adj = expanded(adj_dev)
+                for p in gnn.parameters():
+                    p.grad = None
+                h_train.grad = None
+                out = gnn.gnn(h_train, adj, None, n2g, {}, {})
+                out.mean().backward()
+
+            ms_train, _ = timed(step_train, max(3, args.steps // 4), 2)
+            train = {"ms_per_step": ms_train, "value": E * NUM_LAYERS / (ms_train * 1e-3), "unit": "edges/s (forward + backward)",
+                     "note": "fp32; forward = the fused kernels, backward = native edge-sized kernels on the transposed graph + library GEMMs "
+                             "for the parameter gradients (ptgnn_b200/autograd.py)"}
+        except Exception as e:  # an extra record must never take the headline line down
+            train = {"error": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            gnn.eval()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.dtype == "f32":
         r = cpu_reference_run(batch, gnn, args.agg, steps=3, warmup=1, budget_s=25.0)
@@ -682,7 +709,7 @@ def main():
                     "serial_value": total_edges * NUM_LAYERS / (ms_e2e_serial * 1e-3), "serial_ms_per_step": ms_e2e_serial,
                     "host_enqueue_ms_per_step": host_ms_e2e},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "cpu_baseline": cpu, "row_shard": row_shard,
+            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "cpu_baseline": cpu, "row_shard": row_shard, "train_step": train,
         }
         print(json.dumps(line))
     if world > 1:
