@@ -295,6 +295,15 @@ int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *node_states, c
                                  void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Backward support (host side: ptgnn_b200/autograd.py).  The pointwise half of the GRUCell backward
+ * (torch.nn.GRUCell, gatedmessagepassing.py:69): gi / gh [N, 3H] = gate pre-activations (order r, z, n), h [N, H] the previous
+ * states, grad_out [N, H] the gradient of the new states -> d_gi, d_gh [N, 3H] (gradients of the pre-activations) and
+ * d_h_direct [N, H] = grad_out * z.  The GEMM-shaped products around it use ptgnn_b200_linear_f32.
+ * ---------------------------------------------------------------------------------------------- */
+int ptgnn_b200_gru_gate_grads_f32(const float *gi, const float *gh, const float *h, const float *grad_out, int64_t num_nodes,
+                                  int32_t state_dim, float *d_gi, float *d_gh, float *d_h_direct, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-side minibatch finalisation -- the graph-structure half of GraphNeuralNetworkModel.extend_minibatch_with /
  * finalize_minibatch (ptgnn/neuralmodels/gnn/graphneuralnetwork.py:386-493).  The host concatenates the graphs' LOCAL int32
  * ids (edge sources / targets of one edge type, or reference nodes); item_ptr [G+1] (device, int64) = where each graph's items

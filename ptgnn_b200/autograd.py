@@ -11,7 +11,8 @@ edge-sized work on the native kernels:
   weights ``W_t^T``, states = ``d agg``); max / min -- the routed message gradients times ``W_t`` on the dense kernel, then the
   native scatter-add by source;
 * parameter gradients (``dW_t``, ``dW_ih``, ``dW_hh``): plain ``[out, rows] x [rows, in]`` GEMMs with a huge K (rows = edges or
-  nodes) -- library GEMMs (``torch.matmul`` = cuBLAS), as are the bias column sums.
+  nodes) -- library GEMMs on the tensor cores in the forward's 3xFP16 split (three cuBLAS fp16 GEMMs with fp32 accumulation per
+  product, operands scaled by a power of two first); bias gradients are column sums.
 
 ``MlpMessagePassingLayer`` (default message MLP) follows the same scheme; its node-sized tail (activation, LayerNorm, dense layer:
 mlpmessagepassing.py:114-117) is differentiated by a local ``torch.autograd.grad`` over library ops, and its output Dropout is a torch
@@ -57,25 +58,63 @@ def needs_grad(module: torch.nn.Module, node_states: torch.Tensor) -> bool:
     return torch.is_grad_enabled() and (node_states.requires_grad or any(p.requires_grad for p in module.parameters()))
 
 
+class _exact_fp16_gemms:
+    """cuBLAS fp16 GEMMs with fp32 accumulation all the way (no reduced-precision split-K reductions) while the split products run."""
+
+    def __enter__(self):
+        self.previous = torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction
+        torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction = self.previous
+        return False
+
+
+def _split16(x: torch.Tensor):
+    """fp32 [rows, cols] -> (hi, lo, inv_scale), x ~= (hi + lo / 2048) * inv_scale with hi, lo fp16: the 3xFP16 split of the forward
+    kernels (22 significant bits) after a power-of-two scaling that brings the largest element to ~2^10 -- gradients are routinely
+    below fp16's normal range.  All on the device, no synchronisation."""
+    amax = x.abs().amax().clamp(min=1e-30)
+    scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
+    xs = x * scale
+    hi = xs.half()
+    lo = ((xs - hi.float()) * 2048.0).half()
+    return hi, lo, 1.0 / scale
+
+
+def _mm_t_split(a, b):
+    """A^T B in fp32 accuracy on the tensor cores for A = (hi, lo, inv) [K, M], B = (hi, lo, inv) [K, N]: three library fp16 GEMMs with
+    fp32 accumulation (hi*hi + 2^-11 (hi*lo + lo*hi)) -- the K = edges / nodes parameter-gradient products were 39 % of a training
+    step as fp32 SIMT GEMMs."""
+    a_hi, a_lo, a_inv = a
+    b_hi, b_lo, b_inv = b
+    main = torch.mm(a_hi.t(), b_hi, out_dtype=torch.float32)
+    corr = torch.mm(a_hi.t(), b_lo, out_dtype=torch.float32) + torch.mm(a_lo.t(), b_hi, out_dtype=torch.float32)
+    return (main + corr * (1.0 / 2048.0)) * (a_inv * b_inv)
+
+
+def _rows(split, index):
+    hi, lo, inv = split
+    return hi.index_select(0, index), lo.index_select(0, index), inv
+
+
 def _gru_backward(g, agg, h, w_ih, w_hh, b_ih, b_hh):
     """Gradients of torch.nn.GRUCell (gate order r, z, n) w.r.t. (input, hidden, weight_ih, weight_hh, bias_ih, bias_hh): gate
-    pre-activations and the two input-gradient products on the native dense kernel, gate derivatives pointwise, the parameter
-    gradients ([3H, N] x [N, .], K = num_nodes) as library GEMMs."""
+    pre-activations and the two input-gradient products on the native dense kernel, the gate derivatives in one native pointwise
+    kernel, the parameter gradients ([3H, N] x [N, .], K = num_nodes) as split fp16 library GEMMs."""
     gi = C.linear(agg, w_ih, b_ih)
     gh = C.linear(h, w_hh, b_hh)
-    i_r, i_z, i_n = gi.chunk(3, dim=1)
-    h_r, h_z, h_n = gh.chunk(3, dim=1)
-    r = torch.sigmoid(i_r + h_r)
-    z = torch.sigmoid(i_z + h_z)
-    n = torch.tanh(i_n + r * h_n)
-    d_n_pre = g * (1.0 - z) * (1.0 - n * n)
-    d_z_pre = g * (h - n) * z * (1.0 - z)
-    d_r_pre = d_n_pre * h_n * r * (1.0 - r)
-    d_gi = torch.cat([d_r_pre, d_z_pre, d_n_pre], dim=1)                 # [N, 3H]
-    d_gh = torch.cat([d_r_pre, d_z_pre, d_n_pre * r], dim=1)
-    d_h = g * z + C.linear(d_gh, w_hh.t().contiguous())                  # direct path + through W_hh
+    d_gi, d_gh, d_h = torch.empty_like(gi), torch.empty_like(gh), torch.empty_like(h)
+    with torch.cuda.device(h.device):
+        rc = N.lib().ptgnn_b200_gru_gate_grads_f32(N.ptr(gi), N.ptr(gh), N.ptr(h), N.ptr(g), h.shape[0], h.shape[1], N.ptr(d_gi), N.ptr(d_gh),
+                                                  N.ptr(d_h), N.current_stream(h.device))
+    N.check(rc, "ptgnn_b200_gru_gate_grads_f32")
+    d_h = d_h + C.linear(d_gh, w_hh.t().contiguous())                    # direct path + through W_hh
     d_agg = C.linear(d_gi, w_ih.t().contiguous())                        # [N, D]
-    return d_agg, d_h, d_gi.t() @ agg, d_gh.t() @ h, d_gi.sum(dim=0), d_gh.sum(dim=0)
+    with _exact_fp16_gemms():
+        s_gi, s_gh = _split16(d_gi), _split16(d_gh)
+        d_w_ih, d_w_hh = _mm_t_split(s_gi, _split16(agg)), _mm_t_split(s_gh, _split16(h))
+    return d_agg, d_h, d_w_ih, d_w_hh, d_gi.sum(dim=0), d_gh.sum(dim=0)
 
 
 class _GatedLayerFunction(torch.autograd.Function):
@@ -120,8 +159,10 @@ class _GatedLayerFunction(torch.autograd.Function):
             if reduce_name == "mean":
                 cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
                 d_agg = d_agg / cnt[:, None]
-            for (src, tgt), w in zip(adj, W):
-                d_W.append(d_agg.index_select(0, tgt).t() @ h.index_select(0, src) if src.numel() else torch.zeros_like(w))
+            with _exact_fp16_gemms():
+                s_dagg, s_h = _split16(d_agg), _split16(h)
+                for (src, tgt), w in zip(adj, W):
+                    d_W.append(_mm_t_split(_rows(s_dagg, tgt), _rows(s_h, src)) if src.numel() else torch.zeros_like(w))
             if E > 0:
                 # d h_src[u] = sum over edges (u -> v, type t) of W_t^T d_agg[v]: the forward's aggregation on the transposed graph
                 rev = [(tgt, src) for src, tgt in adj]
@@ -132,6 +173,7 @@ class _GatedLayerFunction(torch.autograd.Function):
             D = d_agg.shape[1]
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)      # row E takes the empty targets' sentinel
             d_msg.scatter_(0, arg, d_agg)                                            # each (edge, feature) has one target: no collisions
+            s_h = _split16(h)
             lo = 0
             for (src, tgt), w in zip(adj, W):
                 e_t = src.numel()
@@ -140,7 +182,8 @@ class _GatedLayerFunction(torch.autograd.Function):
                 if e_t == 0:
                     d_W.append(torch.zeros_like(w))
                     continue
-                d_W.append(part.t() @ h.index_select(0, src))
+                with _exact_fp16_gemms():
+                    d_W.append(_mm_t_split(_split16(part), _rows(s_h, src)))
                 d_h = d_h + scatter_sum(C.linear(part.contiguous(), w.t().contiguous()), src, dim=0, dim_size=num_nodes)
         return (None, None, None, d_h, d_w_ih, d_w_hh, d_b_ih, d_b_hh, *d_W)
 
@@ -218,14 +261,15 @@ class _MlpLayerFunction(torch.autograd.Function):
             if reduce_name == "mean":
                 cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
                 d_agg = (d_agg / cnt[:, None]).contiguous()
-            for (src, tgt), w in zip(adj, W):
-                if src.numel() == 0:
-                    d_W.append(torch.zeros_like(w))
-                    continue
-                rows = h.index_select(0, src)
-                if use_target:
-                    rows = torch.cat([rows, h.index_select(0, tgt)], dim=1)
-                d_W.append(d_agg.index_select(0, tgt).t() @ rows)
+            with _exact_fp16_gemms():
+                s_dagg, s_h = _split16(d_agg), _split16(h)
+                for (src, tgt), w in zip(adj, W):
+                    if src.numel() == 0:
+                        d_W.append(torch.zeros_like(w))
+                        continue
+                    a = _rows(s_dagg, tgt)
+                    d_w = _mm_t_split(a, _rows(s_h, src))                                          # [D, H]: columns multiplying h_src
+                    d_W.append(torch.cat([d_w, _mm_t_split(a, _rows(s_h, tgt))], dim=1) if use_target else d_w)
             if E > 0:
                 rplan = plan_for([(tgt, src) for src, tgt in adj], num_nodes)                     # transposed graph: d h_src
                 back = C.edge_messages(rplan, d_agg, None, [w.t().contiguous() for w in Ws], False)
@@ -238,6 +282,7 @@ class _MlpLayerFunction(torch.autograd.Function):
             D = d_agg.shape[1]
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)
             d_msg.scatter_(0, arg, d_agg)
+            s_h = _split16(h)
             lo = 0
             for t, ((src, tgt), w) in enumerate(zip(adj, W)):
                 e_t = src.numel()
@@ -246,10 +291,10 @@ class _MlpLayerFunction(torch.autograd.Function):
                 if e_t == 0:
                     d_W.append(torch.zeros_like(w))
                     continue
-                rows = h.index_select(0, src)
-                if use_target:
-                    rows = torch.cat([rows, h.index_select(0, tgt)], dim=1)
-                d_W.append(part.t() @ rows)
+                with _exact_fp16_gemms():
+                    a = _split16(part)
+                    d_w = _mm_t_split(a, _rows(s_h, src))
+                    d_W.append(torch.cat([d_w, _mm_t_split(a, _rows(s_h, tgt))], dim=1) if use_target else d_w)
                 d_h = d_h + scatter_sum(C.linear(part, Ws[t].t().contiguous()), src, dim=0, dim_size=num_nodes)
                 if use_target:
                     d_h = d_h + scatter_sum(C.linear(part, Wg[t].t().contiguous()), tgt, dim=0, dim_size=num_nodes)
@@ -283,7 +328,9 @@ class _LinearFn(torch.autograd.Function):
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         g = g.contiguous()
-        return C.linear(g, weight.detach().t().contiguous()), g.t() @ x.detach(), (g.sum(dim=0) if ctx.has_bias else None)
+        with _exact_fp16_gemms():
+            d_w = _mm_t_split(_split16(g), _split16(x.detach()))
+        return C.linear(g, weight.detach().t().contiguous()), d_w, (g.sum(dim=0) if ctx.has_bias else None)
 
 
 class _SegmentReduceFn(torch.autograd.Function):
