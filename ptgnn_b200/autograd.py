@@ -70,16 +70,23 @@ class _exact_fp16_gemms:
         return False
 
 
-def _split16(x: torch.Tensor):
+def _split16(x: torch.Tensor, scaled: bool = True):
     """fp32 [rows, cols] -> (hi, lo, inv_scale), x ~= (hi + lo / 2048) * inv_scale with hi, lo fp16: the 3xFP16 split of the forward
-    kernels (22 significant bits) after a power-of-two scaling that brings the largest element to ~2^10 -- gradients are routinely
-    below fp16's normal range.  All on the device, no synchronisation."""
-    amax = x.abs().amax().clamp(min=1e-30)
-    scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
-    xs = x * scale
-    hi = xs.half()
-    lo = ((xs - hi.float()) * 2048.0).half()
-    return hi, lo, 1.0 / scale
+    kernels (22 significant bits).  scaled: first multiply by the power of two that brings the largest element to ~2^10 -- gradients
+    are routinely below fp16's normal range (states and aggregates are not: the forward already requires them to fit).  All on the
+    device, no synchronisation."""
+    if x.numel() == 0:
+        z = torch.zeros(x.shape, dtype=torch.float16, device=x.device)
+        return z, z, 1.0
+    inv = 1.0
+    if scaled:
+        amax = torch.linalg.vector_norm(x, ord=float("inf")).clamp(min=1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
+        x = x * scale
+        inv = 1.0 / scale
+    hi = x.half()
+    lo = torch.sub(x, hi).mul_(2048.0).half()
+    return hi, lo, inv
 
 
 def _mm_t_split(a, b):
@@ -89,13 +96,20 @@ def _mm_t_split(a, b):
     a_hi, a_lo, a_inv = a
     b_hi, b_lo, b_inv = b
     main = torch.mm(a_hi.t(), b_hi, out_dtype=torch.float32)
-    corr = torch.mm(a_hi.t(), b_lo, out_dtype=torch.float32) + torch.mm(a_lo.t(), b_hi, out_dtype=torch.float32)
-    return (main + corr * (1.0 / 2048.0)) * (a_inv * b_inv)
+    corr = torch.mm(a_hi.t(), b_lo, out_dtype=torch.float32)
+    corr.add_(torch.mm(a_lo.t(), b_hi, out_dtype=torch.float32))
+    return main.add_(corr, alpha=1.0 / 2048.0).mul_(a_inv * b_inv)
 
 
 def _rows(split, index):
+    """Rows `index` of a split tensor (gathered once for ALL edges of a layer; per-type operands are then slices of the result)."""
     hi, lo, inv = split
     return hi.index_select(0, index), lo.index_select(0, index), inv
+
+
+def _slice(split, lo_, hi_):
+    hi, lo, inv = split
+    return hi[lo_:hi_], lo[lo_:hi_], inv
 
 
 def _gru_backward(g, agg, h, w_ih, w_hh, b_ih, b_hh):
@@ -113,7 +127,7 @@ def _gru_backward(g, agg, h, w_ih, w_hh, b_ih, b_hh):
     d_agg = C.linear(d_gi, w_ih.t().contiguous())                        # [N, D]
     with _exact_fp16_gemms():
         s_gi, s_gh = _split16(d_gi), _split16(d_gh)
-        d_w_ih, d_w_hh = _mm_t_split(s_gi, _split16(agg)), _mm_t_split(s_gh, _split16(h))
+        d_w_ih, d_w_hh = _mm_t_split(s_gi, _split16(agg, False)), _mm_t_split(s_gh, _split16(h, False))
     return d_agg, d_h, d_w_ih, d_w_hh, d_gi.sum(dim=0), d_gh.sum(dim=0)
 
 
@@ -160,9 +174,11 @@ class _GatedLayerFunction(torch.autograd.Function):
                 cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
                 d_agg = d_agg / cnt[:, None]
             with _exact_fp16_gemms():
-                s_dagg, s_h = _split16(d_agg), _split16(h)
-                for (src, tgt), w in zip(adj, W):
-                    d_W.append(_mm_t_split(_rows(s_dagg, tgt), _rows(s_h, src)) if src.numel() else torch.zeros_like(w))
+                a_all = _rows(_split16(d_agg), plan.tgt32.long())            # [E, D] rows of d_agg, cat(types) order
+                b_all = _rows(_split16(h, False), plan.src32.long())         # [E, H] source states
+                for t, w in enumerate(W):
+                    lo_, hi_ = plan.type_off[t], plan.type_off[t + 1]
+                    d_W.append(_mm_t_split(_slice(a_all, lo_, hi_), _slice(b_all, lo_, hi_)) if hi_ > lo_ else torch.zeros_like(w))
             if E > 0:
                 # d h_src[u] = sum over edges (u -> v, type t) of W_t^T d_agg[v]: the forward's aggregation on the transposed graph
                 rev = [(tgt, src) for src, tgt in adj]
@@ -173,7 +189,9 @@ class _GatedLayerFunction(torch.autograd.Function):
             D = d_agg.shape[1]
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)      # row E takes the empty targets' sentinel
             d_msg.scatter_(0, arg, d_agg)                                            # each (edge, feature) has one target: no collisions
-            s_h = _split16(h)
+            with _exact_fp16_gemms():
+                a_all = _split16(d_msg[:E])
+                b_all = _rows(_split16(h, False), plan.src32.long())
             lo = 0
             for (src, tgt), w in zip(adj, W):
                 e_t = src.numel()
@@ -183,7 +201,7 @@ class _GatedLayerFunction(torch.autograd.Function):
                     d_W.append(torch.zeros_like(w))
                     continue
                 with _exact_fp16_gemms():
-                    d_W.append(_mm_t_split(_split16(part), _rows(s_h, src)))
+                    d_W.append(_mm_t_split(_slice(a_all, lo - e_t, lo), _slice(b_all, lo - e_t, lo)))
                 d_h = d_h + scatter_sum(C.linear(part.contiguous(), w.t().contiguous()), src, dim=0, dim_size=num_nodes)
         return (None, None, None, d_h, d_w_ih, d_w_hh, d_b_ih, d_b_hh, *d_W)
 
@@ -262,14 +280,18 @@ class _MlpLayerFunction(torch.autograd.Function):
                 cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
                 d_agg = (d_agg / cnt[:, None]).contiguous()
             with _exact_fp16_gemms():
-                s_dagg, s_h = _split16(d_agg), _split16(h)
-                for (src, tgt), w in zip(adj, W):
-                    if src.numel() == 0:
+                s_h = _split16(h, False)
+                tgt_all = plan.tgt32.long()
+                a_all, b_all = _rows(_split16(d_agg), tgt_all), _rows(s_h, plan.src32.long())
+                g_all = _rows(s_h, tgt_all) if use_target else None
+                for t, w in enumerate(W):
+                    lo_, hi_ = plan.type_off[t], plan.type_off[t + 1]
+                    if hi_ == lo_:
                         d_W.append(torch.zeros_like(w))
                         continue
-                    a = _rows(s_dagg, tgt)
-                    d_w = _mm_t_split(a, _rows(s_h, src))                                          # [D, H]: columns multiplying h_src
-                    d_W.append(torch.cat([d_w, _mm_t_split(a, _rows(s_h, tgt))], dim=1) if use_target else d_w)
+                    a = _slice(a_all, lo_, hi_)
+                    d_w = _mm_t_split(a, _slice(b_all, lo_, hi_))                                  # [D, H]: columns multiplying h_src
+                    d_W.append(torch.cat([d_w, _mm_t_split(a, _slice(g_all, lo_, hi_))], dim=1) if use_target else d_w)
             if E > 0:
                 rplan = plan_for([(tgt, src) for src, tgt in adj], num_nodes)                     # transposed graph: d h_src
                 back = C.edge_messages(rplan, d_agg, None, [w.t().contiguous() for w in Ws], False)
@@ -282,7 +304,10 @@ class _MlpLayerFunction(torch.autograd.Function):
             D = d_agg.shape[1]
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)
             d_msg.scatter_(0, arg, d_agg)
-            s_h = _split16(h)
+            with _exact_fp16_gemms():
+                s_h = _split16(h, False)
+                a_all, b_all = _split16(d_msg[:E]), _rows(s_h, plan.src32.long())
+                g_all = _rows(s_h, plan.tgt32.long()) if use_target else None
             lo = 0
             for t, ((src, tgt), w) in enumerate(zip(adj, W)):
                 e_t = src.numel()
@@ -292,9 +317,9 @@ class _MlpLayerFunction(torch.autograd.Function):
                     d_W.append(torch.zeros_like(w))
                     continue
                 with _exact_fp16_gemms():
-                    a = _split16(part)
-                    d_w = _mm_t_split(a, _rows(s_h, src))
-                    d_W.append(torch.cat([d_w, _mm_t_split(a, _rows(s_h, tgt))], dim=1) if use_target else d_w)
+                    a = _slice(a_all, lo - e_t, lo)
+                    d_w = _mm_t_split(a, _slice(b_all, lo - e_t, lo))
+                    d_W.append(torch.cat([d_w, _mm_t_split(a, _slice(g_all, lo - e_t, lo))], dim=1) if use_target else d_w)
                 d_h = d_h + scatter_sum(C.linear(part, Ws[t].t().contiguous()), src, dim=0, dim_size=num_nodes)
                 if use_target:
                     d_h = d_h + scatter_sum(C.linear(part, Wg[t].t().contiguous()), tgt, dim=0, dim_size=num_nodes)
