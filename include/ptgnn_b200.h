@@ -300,6 +300,12 @@ int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *node_states, c
  * states, grad_out [N, H] the gradient of the new states -> d_gi, d_gh [N, 3H] (gradients of the pre-activations) and
  * d_h_direct [N, H] = grad_out * z.  The GEMM-shaped products around it use ptgnn_b200_linear_f32.
  * ---------------------------------------------------------------------------------------------- */
+/* Operand preparation for the parameter-gradient products dW = A^T B (K = edges or nodes; run by the host as three fp16 tensor-core
+ * GEMMs per product): out row r = split(x[index ? index[r] : r] * (scale ? *scale : 1)), split(v) = (hi = rn16(v),
+ * lo = rn16((v - hi) * 2^11)) -- the 3xFP16 representation of csrc/fused_mp.cuh.  x [*, cols] fp32, index int32 (NULL: identity),
+ * scale: device scalar (NULL: 1), hi / lo [rows_out, cols] fp16.  cols % 8 == 0. */
+int ptgnn_b200_gather_split_f16(const float *x, const int32_t *index, int64_t rows_out, int32_t cols, const float *scale, void *hi,
+                                void *lo, void *stream);
 int ptgnn_b200_gru_gate_grads_f32(const float *gi, const float *gh, const float *h, const float *grad_out, int64_t num_nodes,
                                   int32_t state_dim, float *d_gi, float *d_gh, float *d_h_direct, void *stream);
 

@@ -70,22 +70,31 @@ class _exact_fp16_gemms:
         return False
 
 
-def _split16(x: torch.Tensor, scaled: bool = True):
-    """fp32 [rows, cols] -> (hi, lo, inv_scale), x ~= (hi + lo / 2048) * inv_scale with hi, lo fp16: the 3xFP16 split of the forward
-    kernels (22 significant bits).  scaled: first multiply by the power of two that brings the largest element to ~2^10 -- gradients
-    are routinely below fp16's normal range (states and aggregates are not: the forward already requires them to fit).  All on the
-    device, no synchronisation."""
-    if x.numel() == 0:
-        z = torch.zeros(x.shape, dtype=torch.float16, device=x.device)
-        return z, z, 1.0
-    inv = 1.0
+def _split16(x: torch.Tensor, scaled: bool = True, index: Optional[torch.Tensor] = None):
+    """fp32 [rows, cols] -> (hi, lo, inv_scale) with (hi + lo / 2048) * inv_scale ~= x[index] (index: int32 row ids, None = all rows in
+    order); hi, lo fp16: the 3xFP16 split of the forward kernels (22 significant bits).  scaled: first multiply by the power of two
+    that brings the largest element to ~2^10 -- gradients are routinely below fp16's normal range (states and aggregates are not: the
+    forward already requires them to fit).  Gather, scaling and split are one native pass; nothing synchronises."""
+    rows = x.shape[0] if index is None else int(index.shape[0])
+    cols = x.shape[1]
+    hi = torch.empty(rows, cols, dtype=torch.float16, device=x.device)
+    lo = torch.empty(rows, cols, dtype=torch.float16, device=x.device)
+    if rows == 0 or x.numel() == 0:
+        return hi, lo, 1.0
+    scale, inv = None, 1.0
     if scaled:
         amax = torch.linalg.vector_norm(x, ord=float("inf")).clamp(min=1e-30)
-        scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
-        x = x * scale
+        scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax))).to(torch.float32)
         inv = 1.0 / scale
-    hi = x.half()
-    lo = torch.sub(x, hi).mul_(2048.0).half()
+    x = x.contiguous()
+    if cols % 8 != 0:      # rare shapes: torch ops
+        v = x if index is None else x.index_select(0, index.long())
+        v = v * scale if scale is not None else v
+        hi = v.half()
+        return hi, torch.sub(v, hi).mul_(2048.0).half(), inv
+    with torch.cuda.device(x.device):
+        rc = N.lib().ptgnn_b200_gather_split_f16(N.ptr(x), N.ptr(index), rows, cols, N.ptr(scale), N.ptr(hi), N.ptr(lo), N.current_stream(x.device))
+    N.check(rc, "ptgnn_b200_gather_split_f16")
     return hi, lo, inv
 
 
@@ -99,12 +108,6 @@ def _mm_t_split(a, b):
     corr = torch.mm(a_hi.t(), b_lo, out_dtype=torch.float32)
     corr.add_(torch.mm(a_lo.t(), b_hi, out_dtype=torch.float32))
     return main.add_(corr, alpha=1.0 / 2048.0).mul_(a_inv * b_inv)
-
-
-def _rows(split, index):
-    """Rows `index` of a split tensor (gathered once for ALL edges of a layer; per-type operands are then slices of the result)."""
-    hi, lo, inv = split
-    return hi.index_select(0, index), lo.index_select(0, index), inv
 
 
 def _slice(split, lo_, hi_):
@@ -174,8 +177,8 @@ class _GatedLayerFunction(torch.autograd.Function):
                 cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
                 d_agg = d_agg / cnt[:, None]
             with _exact_fp16_gemms():
-                a_all = _rows(_split16(d_agg), plan.tgt32.long())            # [E, D] rows of d_agg, cat(types) order
-                b_all = _rows(_split16(h, False), plan.src32.long())         # [E, H] source states
+                a_all = _split16(d_agg, True, plan.tgt32)                    # [E, D] rows of d_agg, cat(types) order
+                b_all = _split16(h, False, plan.src32)                       # [E, H] source states
                 for t, w in enumerate(W):
                     lo_, hi_ = plan.type_off[t], plan.type_off[t + 1]
                     d_W.append(_mm_t_split(_slice(a_all, lo_, hi_), _slice(b_all, lo_, hi_)) if hi_ > lo_ else torch.zeros_like(w))
@@ -191,7 +194,7 @@ class _GatedLayerFunction(torch.autograd.Function):
             d_msg.scatter_(0, arg, d_agg)                                            # each (edge, feature) has one target: no collisions
             with _exact_fp16_gemms():
                 a_all = _split16(d_msg[:E])
-                b_all = _rows(_split16(h, False), plan.src32.long())
+                b_all = _split16(h, False, plan.src32)
             lo = 0
             for (src, tgt), w in zip(adj, W):
                 e_t = src.numel()
@@ -280,10 +283,8 @@ class _MlpLayerFunction(torch.autograd.Function):
                 cnt = (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(torch.float32)
                 d_agg = (d_agg / cnt[:, None]).contiguous()
             with _exact_fp16_gemms():
-                s_h = _split16(h, False)
-                tgt_all = plan.tgt32.long()
-                a_all, b_all = _rows(_split16(d_agg), tgt_all), _rows(s_h, plan.src32.long())
-                g_all = _rows(s_h, tgt_all) if use_target else None
+                a_all, b_all = _split16(d_agg, True, plan.tgt32), _split16(h, False, plan.src32)
+                g_all = _split16(h, False, plan.tgt32) if use_target else None
                 for t, w in enumerate(W):
                     lo_, hi_ = plan.type_off[t], plan.type_off[t + 1]
                     if hi_ == lo_:
@@ -305,9 +306,8 @@ class _MlpLayerFunction(torch.autograd.Function):
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)
             d_msg.scatter_(0, arg, d_agg)
             with _exact_fp16_gemms():
-                s_h = _split16(h, False)
-                a_all, b_all = _split16(d_msg[:E]), _rows(s_h, plan.src32.long())
-                g_all = _rows(s_h, plan.tgt32.long()) if use_target else None
+                a_all, b_all = _split16(d_msg[:E]), _split16(h, False, plan.src32)
+                g_all = _split16(h, False, plan.tgt32) if use_target else None
             lo = 0
             for t, ((src, tgt), w) in enumerate(zip(adj, W)):
                 e_t = src.numel()

@@ -4,6 +4,8 @@
 //   d_gi = [d_r, d_z, d_n],   d_gh = [d_r, d_z, d_n * r],   d_h_direct = g z
 // with d_n = g (1 - z)(1 - n^2), d_z = g (h - n) z (1 - z), d_r = d_n h_n r (1 - r).  The four GEMM-shaped products around it
 // (gi, gh, d_gi W_ih, d_gh W_hh) run on the dense kernels; as separate torch pointwise ops this was 17 % of a training step.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ptgnn {
@@ -62,6 +64,58 @@ extern "C" int ptgnn_b200_gru_gate_grads_f32(const float *gi, const float *gh, c
         TimedScope timed__(PTGNN_KERNEL_GRU, st);
         gru_gate_grads_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(gi, gh, h, grad_out, num_nodes, state_dim, d_gi, d_gh,
                                                                                                  d_h_direct);
+    }
+    PTGNN_LAUNCHED();
+    return PTGNN_OK;
+}
+
+// Operand preparation for the parameter-gradient GEMMs (dW = A^T B with K = edges or nodes, run as three fp16 tensor-core GEMMs):
+// out row r = split16(x[index ? index[r] : r] * (scale ? *scale : 1)) with split16(v) = (hi = rn16(v), lo = rn16((v - hi) * 2^11)),
+// the forward kernels' 3xFP16 representation.  One pass: gather + scale + split (as separate torch ops -- gather, mul, two casts, sub,
+// mul -- this was a quarter of a training step).
+namespace ptgnn {
+
+__global__ void __launch_bounds__(256) gather_split_kernel(const float *__restrict__ x, const int32_t *__restrict__ index, long long rows, int cols,
+                                                           const float *__restrict__ scale, uint4 *__restrict__ hi, uint4 *__restrict__ lo) {
+    const float s = scale != nullptr ? *scale : 1.0f;
+    const int c8n = cols / 8;
+    const long long total = rows * c8n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c8n;
+        const int c8 = (int)(i - r * c8n);
+        const long long src_row = index != nullptr ? (long long)index[r] : r;
+        const float4 a = *reinterpret_cast<const float4 *>(x + src_row * cols + c8 * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(x + src_row * cols + c8 * 8 + 4);
+        const float v[8] = {a.x * s, a.y * s, a.z * s, a.w * s, b.x * s, b.y * s, b.z * s, b.w * s};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 h2 = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+            const float2 f2 = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn((v[2 * k] - f2.x) * 2048.0f, (v[2 * k + 1] - f2.y) * 2048.0f);
+            h[k] = *reinterpret_cast<const uint32_t *>(&h2);
+            l[k] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        hi[r * c8n + c8] = make_uint4(h[0], h[1], h[2], h[3]);
+        lo[r * c8n + c8] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+}  // namespace ptgnn
+
+extern "C" int ptgnn_b200_gather_split_f16(const float *x, const int32_t *index, int64_t rows_out, int32_t cols, const float *scale, void *hi,
+                                           void *lo, void *stream) {
+    using namespace ptgnn;
+    PTGNN_CHECK_ARG(rows_out >= 0 && cols > 0 && cols % 8 == 0, "gather_split: cols=%d must be a positive multiple of 8", cols);
+    if (rows_out == 0) return PTGNN_OK;
+    PTGNN_CHECK_ARG(x && hi && lo, "gather_split: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = (long long)rows_out * (cols / 8);
+    const long long blocks = (total + 255) / 256;
+    {
+        TimedScope timed__(PTGNN_KERNEL_PACK, st);
+        gather_split_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(x, index, rows_out, cols, scale, static_cast<uint4 *>(hi),
+                                                                                               static_cast<uint4 *>(lo));
     }
     PTGNN_LAUNCHED();
     return PTGNN_OK;
