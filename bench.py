@@ -403,8 +403,11 @@ def main():
         and the D2H of step i-1 overlap the kernels of step i -- what the reference's own background minibatch threads do
         (`ptgnn/baseneuralmodel/abstractneuralmodel.py:348-357`)."""
 
-        def __init__(self, graphed: bool = False):
+        def __init__(self, graphed: bool = False, pooled: bool = False):
             self.graphed = graphed           # replay GraphNeuralNetwork.capture() graphs (one per input buffer) instead of eager calls
+            self.pooled = pooled             # result read back = per-graph mean of the output states (a Graph2Class-style readout on the
+                                             # native scatter kernel) instead of all node states
+            self.pool_host = [torch.empty(batch.num_graphs, HIDDEN, dtype=torch.float32).pin_memory() for _ in range(2)]
             self.graphs = [None, None]
             self.h2d, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.h_buf = [torch.empty_like(h_dev) for _ in range(2)]
@@ -443,11 +446,16 @@ def main():
                     res = gnn(node_data={"input": self.h_buf[k]}, adjacency_lists=list(self.adj_buf[k]), edge_feature_data=[],
                               node_to_graph_idx=n2g, reference_node_ids={}, reference_node_graph_idx={}, num_graphs=batch.num_graphs)
                 out = res.output_node_representations
+            result, result_host = out, self.out_host[k]
+            if self.pooled:
+                result, result_host = P.scatter_mean(out.float(), n2g, dim=0, dim_size=batch.num_graphs), self.pool_host[k]
             self.compute_done[k].record(main)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(self.compute_done[k])
-                self.out_host[k].copy_(out, non_blocking=True)
+                result_host.copy_(result, non_blocking=True)
                 self.d2h_done[k].record(self.d2h)
+            if self.pooled:
+                result.record_stream(self.d2h)
             if not self.graphed:
                 out.record_stream(self.d2h)
             self.keep[k] = out
@@ -513,6 +521,17 @@ def main():
             graph_info = {"error": repr(exc)[:300]}
     else:
         graph_info = None
+    # extra record: the same loop when the result read back is a per-graph readout (41 KB) instead of all node states (105 MB) --
+    # what a graph-level model actually returns; shows how much of the multi-GPU e2e figure is the host link
+    pooled_info = None
+    if not args.no_graphs:
+        try:
+            ppipe = PipelinedE2E(graphed=True, pooled=True)
+            ms_p, _ = timed(ppipe.step, args.steps, max(args.warmup, 4), finish=ppipe.finish)
+            pooled_info = {"ms_per_step": ms_p, "value": E * world * NUM_LAYERS / (ms_p * 1e-3), "d2h_bytes_per_step": batch.num_graphs * HIDDEN * 4,
+                           "result": "per-graph mean of the output node states (ptgnn_b200.scatter_mean), fp32"}
+        except Exception as exc:
+            pooled_info = {"error": repr(exc)[:300]}
 
     total_edges = E * world
     value = total_edges * NUM_LAYERS / (ms_step * 1e-3)
@@ -705,7 +724,7 @@ def main():
                             (" (GraphNeuralNetwork.capture: plan build + 8 layers replayed as one CUDA graph)" if e2e_mode == "cuda-graph" else ""),
                     "eager_pipelined": {"value": total_edges * NUM_LAYERS / (ms_e2e_eager * 1e-3), "ms_per_step": ms_e2e_eager,
                                         "host_enqueue_ms_per_step": host_ms_eager},
-                    "cuda_graph_pipelined": graph_info,
+                    "cuda_graph_pipelined": graph_info, "cuda_graph_pipelined_pooled_result": pooled_info,
                     "serial_value": total_edges * NUM_LAYERS / (ms_e2e_serial * 1e-3), "serial_ms_per_step": ms_e2e_serial,
                     "host_enqueue_ms_per_step": host_ms_e2e},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
