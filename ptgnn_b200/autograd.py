@@ -27,6 +27,7 @@ from typing import List, Optional, Tuple
 
 import torch
 import torch.nn.functional as F_
+from torch.autograd.function import once_differentiable
 
 from . import _native as N
 from . import composed as C
@@ -145,6 +146,7 @@ class _GatedLayerFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable          # the backward runs native kernels: no double backward
     def backward(ctx, grad_out):
         h, w_ih, w_hh, b_ih, b_hh, *weights = ctx.saved_tensors
         adj: List[Tuple[torch.Tensor, torch.Tensor]] = ctx.adjacency_lists
@@ -240,6 +242,7 @@ class _MlpLayerFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable          # the backward runs native kernels: no double backward
     def backward(ctx, grad_out):
         h, *params = ctx.saved_tensors
         tail_params, weights = params[:ctx.num_tail_params], params[ctx.num_tail_params:]
@@ -350,6 +353,7 @@ class _LinearFn(torch.autograd.Function):
         return C.linear(x.detach().contiguous(), weight.detach().contiguous(), None if bias is None else bias.detach())
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         g = g.contiguous()
@@ -373,6 +377,7 @@ class _SegmentReduceFn(torch.autograd.Function):
         return C.segment_reduce(m, plan, N.REDUCE[reduce_name])
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         plan, reduce_name = ctx.plan, ctx.reduce_name
         g = g.contiguous()
@@ -398,6 +403,7 @@ class _GRUCellFn(torch.autograd.Function):
         return C.grucell(agg.detach().contiguous(), h.detach().contiguous(), shim)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         agg, h, w_ih, w_hh, b_ih, b_hh = (t.detach() for t in ctx.saved_tensors)
         return _gru_backward(g.contiguous(), agg.contiguous(), h.contiguous(), w_ih.contiguous(), w_hh.contiguous(), b_ih, b_hh)
