@@ -13,7 +13,39 @@ import torch
 from . import _native as N
 
 
-def _run(src: torch.Tensor, index: torch.Tensor, dim: int, dim_size: Optional[int], reduce: str, want_arg: bool):
+_LONG_SEGMENT_ROWS = 1024      # average rows per output row from which the two-level reduction is used (readout-style calls)
+
+
+def _run_two_level(src: torch.Tensor, index: torch.Tensor, dim_size: int, reduce: str):
+    """Few, very long segments (graph-level readouts: node_to_graph_idx has ~10^2 targets for ~10^5 rows).  The segmented-reduce
+    kernel parallelises over TARGET rows, so such a call would run on a handful of warps (measured: 28 ms for 204,800 x 128 -> 80).
+    Two levels of the same kernel instead: every segment is cut, in its stable sorted order, into sub-segments of `chunk` rows
+    (level 1: <= ~65k sub-targets), whose partial results are reduced per target (level 2).  sum / mean re-associate the fp32
+    sum by chunks (max / min are exact); arg outputs are not offered on this path."""
+    from .edgeplan import EdgePlan
+
+    E, D = src.shape
+    chunk = max(256, -(-E * dim_size // 65536))
+    C = -(-E // chunk)                                            # sub-segments per target (upper bound: one target owning every row)
+    plan = EdgePlan([(index, index)], dim_size)                   # row_ptr + stable sorted positions; reports out-of-range indices
+    row_ptr = plan.row_ptr.long()
+    rank = plan.pos.long() - row_ptr[:-1].index_select(0, plan.tgt32.long())   # position inside the target's segment
+    sub = plan.tgt32.long() * C + torch.div(rank, chunk, rounding_mode="floor")
+    level = "sum" if reduce in ("sum", "mean") else reduce
+    part, _ = _run(src, sub, 0, dim_size * C, level, False, two_level=False)
+    if level != "sum":         # empty sub-segments hold 0 (torch_scatter's convention): make them lose against every real value
+        filled = torch.bincount(sub, minlength=dim_size * C) > 0
+        lowest = torch.finfo(torch.float32).min if level == "max" else torch.finfo(torch.float32).max
+        part = torch.where(filled[:, None], part, torch.full_like(part, lowest))
+    owner = torch.arange(dim_size * C, dtype=torch.int64, device=src.device) // C
+    out, _ = _run(part, owner, 0, dim_size, level, False, two_level=False)
+    if reduce == "mean":
+        out = out / (row_ptr[1:] - row_ptr[:-1]).clamp(min=1).to(torch.float32)[:, None]
+    plan.poll()
+    return out, None
+
+
+def _run(src: torch.Tensor, index: torch.Tensor, dim: int, dim_size: Optional[int], reduce: str, want_arg: bool, two_level: bool = True):
     if src.dim() != 2 or dim not in (0, -2) or index.dim() != 1:
         raise NotImplementedError("native scatter supports src [E, D] reduced along dim=0 with a 1-D index")
     src = N.require_cuda(src, "src", torch.float32)
@@ -23,6 +55,8 @@ def _run(src: torch.Tensor, index: torch.Tensor, dim: int, dim_size: Optional[in
         raise ValueError("index and src disagree on the number of rows")
     if dim_size is None:
         dim_size = int(index.max().item()) + 1 if E else 0
+    if two_level and not want_arg and dim_size > 0 and E >= 32768 and E // dim_size >= _LONG_SEGMENT_ROWS:
+        return _run_two_level(src, index, dim_size, reduce)
     lib = N.lib()
     out = torch.empty(dim_size, D, dtype=torch.float32, device=src.device)
     arg = torch.empty(dim_size, D, dtype=torch.int64, device=src.device) if want_arg else None
