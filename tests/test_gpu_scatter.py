@@ -23,6 +23,10 @@ def _check(src, idx, n, reduce):
         assert torch.equal(arg.cpu(), ref_arg), f"{reduce}: arg (first occurrence) must be bit-exact"
         assert torch.equal(P.scatter(src.cuda(), idx.cuda(), dim=0, dim_size=n, reduce=reduce).cpu(), ref)
     else:
+        if src.shape[0] >= 32768 and src.shape[0] // max(n, 1) >= 1024:
+            # readout-shaped call: the two-level path re-associates the fp32 sum by chunks, the CPU reference adds sequentially (its own
+            # rounding error over thousands of rows is ~1e-4): judge both against the float64 result
+            ref = O.scatter_with_arg(src.double(), idx, n, reduce)[0].float()
         mask = ~torch.isnan(ref)
         assert torch.equal(torch.isnan(out.cpu()), ~mask)
         assert_close(torch.nan_to_num(out.cpu()), torch.nan_to_num(ref), what=reduce)
@@ -84,7 +88,7 @@ def test_readout_shaped_scatter_uses_the_two_level_path(reduce):
     gen = torch.Generator().manual_seed(1)
     src = torch.randn(204800, 128, generator=gen)
     for index, n in ((torch.arange(204800) // 2560, 80), (torch.randint(0, 40, (204800,), generator=gen) * 2, 81)):
-        ref = O.scatter(src, index, n, reduce)
+        ref = O.scatter(src.double(), index, n, reduce).float()      # float64 reference: see _check
         got = P.scatter(src.cuda(), index.cuda(), dim=0, dim_size=n, reduce=reduce)
         err = ((got.cpu() - ref).abs() / ref.abs().clamp(min=1)).max().item()
         assert err <= (0 if reduce in ("max", "min") else 1e-5), f"{reduce}: {err:.3e}"
