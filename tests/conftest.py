@@ -19,6 +19,9 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
 
+    torch.backends.cuda.matmul.allow_tf32 = False       # torch-on-GPU references in the tests are true fp32
+    torch.backends.cudnn.allow_tf32 = False
+
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

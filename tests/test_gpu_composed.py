@@ -32,7 +32,23 @@ def test_mlp_module_forward():
                 ref = mlp.activation(ref)
         with torch.no_grad():
             got = mlp.cuda()(x.cuda())
-        assert_close(got, ref.detach(), what=f"MLP {kw}")
+            err = ((got.cpu() - ref.detach()).abs() / ref.detach().abs().clamp(min=1)).max().item()
+            if err > 1e-5:
+                # Seen on some GPU boxes only (2 of 7 sessions, and not on every run there): the CPU reference of this tiny chain differs
+                # by ~7e-5 while the native result is unchanged.  Judge against a second, independent fp32 reference (the same chain in
+                # torch on the GPU, TF32 off) before calling it a failure, and print what disagreed.
+                gpu_ref = x.cuda()
+                for i, l in enumerate(mlp.linears):
+                    gpu_ref = F.linear(gpu_ref, l.weight, l.bias)
+                    if i + 1 < len(mlp.linears):
+                        gpu_ref = mlp.activation(gpu_ref)
+                err_gpu = ((got - gpu_ref).abs() / gpu_ref.abs().clamp(min=1)).max().item()
+                print(f"\nDIAG {kw}: native vs CPU reference {err:.3e}; native vs torch-on-GPU reference {err_gpu:.3e}; "
+                      f"torch-on-GPU vs CPU reference {(gpu_ref.cpu() - ref.detach()).abs().max().item():.3e}; "
+                      f"native twice equal: {torch.equal(got, mlp(x.cuda()))}; CPU threads {torch.get_num_threads()}")
+                assert err_gpu <= 1e-5, f"MLP {kw}: max scaled error {err:.3e} (CPU reference), {err_gpu:.3e} (GPU reference)"
+            else:
+                assert_close(got, ref.detach(), what=f"MLP {kw}")
 
 
 @pytest.mark.parametrize("agg", ["sum", "max"])
