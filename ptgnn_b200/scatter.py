@@ -19,28 +19,35 @@ _LONG_SEGMENT_ROWS = 1024      # average rows per output row from which the two-
 def _run_two_level(src: torch.Tensor, index: torch.Tensor, dim_size: int, reduce: str):
     """Few, very long segments (graph-level readouts: node_to_graph_idx has ~10^2 targets for ~10^5 rows).  The segmented-reduce
     kernel parallelises over TARGET rows, so such a call would run on a handful of warps (measured: 28 ms for 204,800 x 128 -> 80).
-    Two levels of the same kernel instead: every segment is cut, in its stable sorted order, into sub-segments of `chunk` rows
-    (level 1: <= ~65k sub-targets), whose partial results are reduced per target (level 2).  sum / mean re-associate the fp32
-    sum by chunks (max / min are exact); arg outputs are not offered on this path."""
+    Two levels of the same kernel instead: every segment is cut, in its stable sorted order, into sub-segments of `chunk` ~
+    sqrt(average segment length) rows, numbered compactly (exclusive scan of the per-target chunk counts, all on the device, no
+    synchronisation); level 1 reduces the sub-segments, level 2 the partial results of each target.  sum / mean re-associate the
+    fp32 sum by chunks (max / min are exact); arg outputs are not offered on this path."""
     from .edgeplan import EdgePlan
 
     E, D = src.shape
-    chunk = max(256, -(-E * dim_size // 65536))
-    C = -(-E // chunk)                                            # sub-segments per target (upper bound: one target owning every row)
+    chunk = max(64, min(1024, int((E / max(dim_size, 1)) ** 0.5)))
     plan = EdgePlan([(index, index)], dim_size)                   # row_ptr + stable sorted positions; reports out-of-range indices
+    tgt = plan.tgt32.long()
     row_ptr = plan.row_ptr.long()
-    rank = plan.pos.long() - row_ptr[:-1].index_select(0, plan.tgt32.long())   # position inside the target's segment
-    sub = plan.tgt32.long() * C + torch.div(rank, chunk, rounding_mode="floor")
+    count = row_ptr[1:] - row_ptr[:-1]
+    chunks = (count + (chunk - 1)) // chunk                       # sub-segments of every target
+    first = torch.cumsum(chunks, 0) - chunks                      # ... and the id of its first one
+    rank = plan.pos.long() - row_ptr[:-1].index_select(0, tgt)    # position of a row inside its target's segment
+    sub = first.index_select(0, tgt) + torch.div(rank, chunk, rounding_mode="floor")
+    num_sub = E // chunk + dim_size                               # upper bound of sum(chunks), known without a device read
     level = "sum" if reduce in ("sum", "mean") else reduce
-    part, _ = _run(src, sub, 0, dim_size * C, level, False, two_level=False)
-    if level != "sum":         # empty sub-segments hold 0 (torch_scatter's convention): make them lose against every real value
-        filled = torch.bincount(sub, minlength=dim_size * C) > 0
+    part, _ = _run(src, sub, 0, num_sub, level, False, two_level=False)
+    owner = torch.zeros(num_sub, dtype=torch.int64, device=src.device)
+    owner.index_put_((sub,), tgt)                                 # duplicates write the same value; unused ids stay with target 0 ...
+    if level != "sum":         # ... where, like every empty sub-segment (torch_scatter's 0), they must lose against every real value
+        filled = torch.zeros(num_sub, dtype=torch.bool, device=src.device)
+        filled.index_fill_(0, sub, True)
         lowest = torch.finfo(torch.float32).min if level == "max" else torch.finfo(torch.float32).max
         part = torch.where(filled[:, None], part, torch.full_like(part, lowest))
-    owner = torch.arange(dim_size * C, dtype=torch.int64, device=src.device) // C
     out, _ = _run(part, owner, 0, dim_size, level, False, two_level=False)
     if reduce == "mean":
-        out = out / (row_ptr[1:] - row_ptr[:-1]).clamp(min=1).to(torch.float32)[:, None]
+        out = out / count.clamp(min=1).to(torch.float32)[:, None]
     plan.poll()
     return out, None
 
