@@ -40,9 +40,12 @@ class MinibatchAssembler:
         adj = tensorized_datapoint.adjacency_lists
         assert len(adj) == self.num_edge_types, "one adjacency list per edge type is required"
         graph_idx = len(partial_minibatch["num_nodes_per_graph"])
+        num_nodes = int(tensorized_datapoint.num_nodes)
+        if not 0 <= num_nodes < 2 ** 31:
+            raise ValueError("a graph's node count must fit int32 (local ids travel as int32)")
         for (src, tgt), (mb_src, mb_tgt) in zip(adj, partial_minibatch["adjacency_lists"]):
             assert len(src) == len(tgt)
-            mb_src.append(np.asarray(src))        # LOCAL ids: the node offset is added on the device
+            mb_src.append(np.asarray(src))        # LOCAL ids (< num_nodes of this graph): the node offset is added on the device
             mb_tgt.append(np.asarray(tgt))
         for ref_name, ref_nodes in tensorized_datapoint.reference_nodes.items():
             partial_minibatch["reference_node_ids"].setdefault(ref_name, []).append((graph_idx, np.asarray(ref_nodes)))
