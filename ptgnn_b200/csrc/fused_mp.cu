@@ -652,13 +652,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fused_aggregate_kernel(const _
                     // column order, so a target's messages are still combined one by one in plan order.  Columns of the other
                     // group are computed but never stored; this group's first column always starts a segment.
                     float t[W];
+                    constexpr bool ADD = RED == PTGNN_REDUCE_SUM || RED == PTGNN_REDUCE_MEAN;
 #pragma unroll
-                    for (int c = 0; c < W; ++c) {
-                        float v = __uint_as_float(vm[c]);
-                        if (NPROD == 3) v = fmaf(__uint_as_float(vc[c]), 1.0f / 2048.0f, v);
-                        else v = __bfloat162float(__float2bfloat16_rn(v));     // the autocast Linear's bf16 output
-                        vm[c] = __float_as_uint(v);
-                        t[c] = red_op<RED>(pre[c], v);
+                    for (int c = 0; c < W; c += 2) {       // two columns per instruction: Blackwell's packed fp32 FMA / ADD (same rounding)
+                        float2 v = make_float2(__uint_as_float(vm[c]), __uint_as_float(vm[c + 1]));
+                        if (NPROD == 3) {
+                            v = __ffma2_rn(make_float2(__uint_as_float(vc[c]), __uint_as_float(vc[c + 1])), make_float2(1.0f / 2048.0f, 1.0f / 2048.0f), v);
+                        } else {                                   // the autocast Linear's bf16 output
+                            v.x = __bfloat162float(__float2bfloat16_rn(v.x));
+                            v.y = __bfloat162float(__float2bfloat16_rn(v.y));
+                        }
+                        vm[c] = __float_as_uint(v.x); vm[c + 1] = __float_as_uint(v.y);
+                        if (ADD) {
+                            const float2 s2 = __fadd2_rn(make_float2(pre[c], pre[c + 1]), v);
+                            t[c] = s2.x; t[c + 1] = s2.y;
+                        } else {
+                            t[c] = red_op<RED>(pre[c], v.x); t[c + 1] = red_op<RED>(pre[c + 1], v.y);
+                        }
                     }
                     continue_segment<RED>(t[0], acc, __uint_as_float(vm[0]), startw & 1u);
 #pragma unroll
