@@ -163,3 +163,43 @@ def test_bench_clock_summary_decodes_nvml_reason_bits():
     out = s.summary()
     assert out["sm_mhz"] == 1965 and out["sm_max_mhz"] == 1965 and out["samples"] == 4
     assert out["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"] and out["power_w_max"] == 330.0
+
+
+def test_state_chain_bookkeeping_without_gpu(monkeypatch):
+    """edgeplan.state_chain: per-thread slot keyed on tensor identity + version; nests; PTGNN_B200_CHAIN=0 hides it; other threads
+    never see it.  (What the layers do with it: tests/test_gpu_round2.py::test_state_chain_*.)"""
+    import threading
+
+    from ptgnn_b200 import edgeplan as EP
+
+    assert EP.current_state_chain() is None
+    out, packed = torch.zeros(4, 8), torch.zeros(4, 32, dtype=torch.uint8)
+    with EP.state_chain() as chain:
+        assert EP.current_state_chain() is chain and chain.lookup(out) is None
+        chain.store(out, packed)
+        assert chain.lookup(out) is packed
+        assert chain.lookup(out.clone()) is None                     # identity, not equality
+        seen = []
+        t = threading.Thread(target=lambda: seen.append(EP.current_state_chain()))
+        t.start(); t.join()
+        assert seen == [None]                                        # per thread
+        with EP.state_chain() as inner:
+            assert EP.current_state_chain() is inner and inner.lookup(out) is None
+        assert EP.current_state_chain() is chain
+        out.add_(1.0)                                                # in-place edit: the packed copy is stale
+        assert chain.lookup(out) is None
+        chain.store(out, None)                                       # a layer that produced no packed form clears the slot
+        assert chain.lookup(out) is None
+        monkeypatch.setenv("PTGNN_B200_CHAIN", "0")
+        assert EP.current_state_chain() is None
+        monkeypatch.delenv("PTGNN_B200_CHAIN")
+    assert EP.current_state_chain() is None
+
+
+def test_minibatch_assembler_is_exported_and_egc_has_the_reference_signature():
+    egc = list(inspect.signature(P.EGCMessagePassingLayer.__init__).parameters)
+    assert egc == ["self", "input_state_dimension", "output_state_dimension", "num_edge_types", "message_aggregation_function",
+                   "num_bases", "num_heads", "dropout_rate"]
+    asm = P.MinibatchAssembler(3, stop_extending_minibatch_after_num_nodes=7)
+    mb = asm.initialize_minibatch()
+    assert sorted(mb) == ["adjacency_lists", "num_nodes_in_mb", "num_nodes_per_graph", "reference_node_ids"] and len(mb["adjacency_lists"]) == 3
