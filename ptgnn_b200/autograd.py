@@ -161,13 +161,13 @@ class _GatedLayerFunction(torch.autograd.Function):
         E = plan.num_edges
 
         # ---- 1. re-compute the aggregate (and, for max / min, which edge won each (target, feature))
-        msg = C.edge_messages(plan, h, None, W, False)                       # [E, D], cat(types) order
         arg = None
         if reduce_name in ("max", "min"):
+            msg = C.edge_messages(plan, h, None, W, False)                   # [E, D], cat(types) order
             agg, arg = C.segment_reduce(msg, plan, reduce, return_arg=True)
+            del msg
         else:
-            agg = C.segment_reduce(msg, plan, reduce)
-        del msg
+            agg = C.aggregate(plan, h, W, reduce)                            # the fused kernel where it takes the dimensions
 
         # ---- 2. GRUCell backward
         d_agg, d_h, d_w_ih, d_w_hh, d_b_ih, d_b_hh = _gru_backward(g, agg, h, w_ih, w_hh, b_ih.detach(), b_hh.detach())
@@ -188,8 +188,7 @@ class _GatedLayerFunction(torch.autograd.Function):
                 # d h_src[u] = sum over edges (u -> v, type t) of W_t^T d_agg[v]: the forward's aggregation on the transposed graph
                 rev = [(tgt, src) for src, tgt in adj]
                 rplan = plan_for(rev, num_nodes)
-                back = C.edge_messages(rplan, d_agg.contiguous(), None, [w.t().contiguous() for w in W], False)   # [E, H]
-                d_h = d_h + C.segment_reduce(back, rplan, N.REDUCE["sum"])
+                d_h = d_h + C.aggregate(rplan, d_agg.contiguous(), [w.t().contiguous() for w in W], N.REDUCE["sum"])
         else:
             D = d_agg.shape[1]
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)      # row E takes the empty targets' sentinel
@@ -298,12 +297,10 @@ class _MlpLayerFunction(torch.autograd.Function):
                     d_W.append(torch.cat([d_w, _mm_t_split(a, _slice(g_all, lo_, hi_))], dim=1) if use_target else d_w)
             if E > 0:
                 rplan = plan_for([(tgt, src) for src, tgt in adj], num_nodes)                     # transposed graph: d h_src
-                back = C.edge_messages(rplan, d_agg, None, [w.t().contiguous() for w in Ws], False)
-                d_h = d_h + C.segment_reduce(back, rplan, N.REDUCE["sum"])
+                d_h = d_h + C.aggregate(rplan, d_agg, [w.t().contiguous() for w in Ws], N.REDUCE["sum"])
                 if use_target:                                                                     # d h_tgt: every edge sends W_g^T d_agg[v] to its own target v
                     tplan = plan_for([(tgt, tgt) for _src, tgt in adj], num_nodes)
-                    back = C.edge_messages(tplan, d_agg, None, [w.t().contiguous() for w in Wg], False)
-                    d_h = d_h + C.segment_reduce(back, tplan, N.REDUCE["sum"])
+                    d_h = d_h + C.aggregate(tplan, d_agg, [w.t().contiguous() for w in Wg], N.REDUCE["sum"])
         else:
             D = d_agg.shape[1]
             d_msg = torch.zeros(E + 1, D, dtype=torch.float32, device=h.device)

@@ -95,6 +95,34 @@ def segment_reduce(messages: torch.Tensor, plan: EdgePlan, reduce_code: int, ret
     return (out, arg) if return_arg else out
 
 
+def aggregate(plan: EdgePlan, source_rows: torch.Tensor, weights: Sequence[torch.Tensor], reduce_code: int) -> torch.Tensor:
+    """``reduce_{e -> v} W_type(e) source_rows[src(e)]`` as [num_nodes, D] fp32: the fused gather -> Linear -> segmented-reduce kernel
+    where it takes the dimensions (D == 128, K in {64, 128}: no [E, D] message tensor), else ``edge_messages`` + ``segment_reduce``.
+    Used by the backward passes (aggregate re-computation; d h_src on the transposed graph)."""
+    import ctypes
+    import os
+
+    D, K = weights[0].shape
+    lib = N.lib()
+    fused_ok = (plan.num_edges > 0 and os.environ.get("PTGNN_B200_FUSED", "1") != "0" and os.environ.get("PTGNN_B200_FP32_MODE", "") != "tf32"
+                and bool(lib.ptgnn_b200_fused_supported(0, K, D)))
+    if not fused_ok:
+        return segment_reduce(edge_messages(plan, source_rows, None, weights, False), plan, reduce_code)
+    rows = N.require_cuda(source_rows, "source_rows", torch.float32)
+    ws_list = [N.require_cuda(w, "edge weight", torch.float32) for w in weights]
+    n = plan.num_nodes
+    ws_bytes = lib.ptgnn_b200_mlp_fused_workspace_bytes(0, n, n, plan.num_types, K, D, D, 0)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=rows.device)
+    out = torch.empty(n, D, dtype=torch.float32, device=rows.device)
+    bp = plan.block_plan()
+    with torch.cuda.device(rows.device):       # the Mlp entry point without activation / LayerNorm / dense layer = the bare aggregation
+        rc = lib.ptgnn_b200_mlp_forward_fused(0, N.ptr(rows), None, n, n, K, D, D, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
+                                              N.ptr_table(ws_list), 0, reduce_code, N.ACT_NONE, None, None, 0.0, None, None, N.ACT_NONE,
+                                              N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(rows.device))
+    N.check(rc, "ptgnn_b200_mlp_forward_fused")
+    return out
+
+
 def grucell(inp: torch.Tensor, hidden: torch.Tensor, gru: nn.GRUCell) -> torch.Tensor:
     rows, H = hidden.shape
     D = inp.shape[1]
