@@ -294,6 +294,20 @@ int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *node_states, c
                                  int32_t dense_activation, void *out_states, void *workspace, size_t workspace_bytes,
                                  void *stream);
 
+/* ptgnn_b200_mlp_forward_fused with caller-owned derived weights (fp32 states): weight_cache [>= ptgnn_b200_mlp_fused_weight_cache_bytes]
+ * holds the packed edge weights and the split dense weight; pass cache_valid = 0 after the parameters changed (they are then
+ * re-derived into the cache), 1 to reuse them.  weight_cache == NULL or bf16 states: identical to ptgnn_b200_mlp_forward_fused. */
+size_t ptgnn_b200_mlp_fused_weight_cache_bytes(int32_t bf16_states, int32_t num_types, int32_t in_dim, int32_t message_dim, int32_t out_dim,
+                                               int32_t use_target_state);
+int ptgnn_b200_mlp_forward_fused_cached(int32_t bf16_states, const void *node_states, const void *gather_states /* NULL: node_states */,
+                                        int64_t num_nodes, int64_t num_source_nodes, int32_t in_dim, int32_t message_dim,
+                                        int32_t out_dim, int32_t num_types, const ptgnn_b200_block_plan *block_plan,
+                                        const int32_t *row_ptr, const float *const *edge_weights /*[host] T device pointers, fp32*/,
+                                        int32_t use_target_state, int32_t reduce, int32_t message_activation, const float *ln_weight,
+                                        const float *ln_bias, float ln_eps, const float *dense_weight, const float *dense_bias,
+                                        int32_t dense_activation, void *out_states, void *workspace, size_t workspace_bytes,
+                                        void *weight_cache, size_t weight_cache_bytes, int32_t cache_valid, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward support (host side: ptgnn_b200/autograd.py).  The pointwise half of the GRUCell backward
  * (torch.nn.GRUCell, gatedmessagepassing.py:69): gi / gh [N, 3H] = gate pre-activations (order r, z, n), h [N, H] the previous

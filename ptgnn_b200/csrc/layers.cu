@@ -285,8 +285,8 @@ static bool tc_enabled() {
 // of the source states (Ns rows) and the TMEM-layout edge weights of the fused kernel.
 // out = act(y W^T + b): tensor cores (3xTF32) when the dims fit the tiles, FFMA tiles otherwise.  scratch >= tc::dense_split_bytes.
 static int dense_any(const float *y, int64_t rows, int D, const float *W, const float *bias, int out_dim, int act, float *out,
-                     void *scratch, cudaStream_t st) {
-    if (tc_enabled() && tc::supported_dense(D, out_dim)) return tc::dense_update(y, rows, D, W, bias, out_dim, act, out, scratch, st);
+                     void *scratch, cudaStream_t st, bool pack = true) {
+    if (tc_enabled() && tc::supported_dense(D, out_dim)) return tc::dense_update(y, rows, D, W, bias, out_dim, act, out, scratch, st, pack);
     int rc;
     if (out_dim <= 64) {
         using Tile = GemmTile<4>;
@@ -543,6 +543,10 @@ extern "C" size_t ptgnn_b200_mlp_workspace_bytes(int64_t num_nodes, int64_t num_
     return mlp_ws_layout(num_nodes, num_nodes, num_edges, num_types, in_dim, message_dim, out_dim, use_target_state, false, false).total;
 }
 
+static size_t mlp_fused_cache_bytes(int T, int H, int D, int out_dim, int ut) {
+    return ws_slice(fused::packed_weight_bytes(3, T, H, ut), 1) + tc::dense_split_bytes(out_dim > 0 ? out_dim : D, D) + 256;
+}
+
 static int mlp_forward_impl(const float *node_states, const float *gather_states, int64_t num_nodes,
                                           int32_t in_dim,
                                           int32_t message_dim, int32_t out_dim, int32_t num_types,
@@ -552,7 +556,8 @@ static int mlp_forward_impl(const float *node_states, const float *gather_states
                                           const float *ln_weight, const float *ln_bias, float ln_eps,
                                           const float *dense_weight, const float *dense_bias, int32_t dense_activation,
                                           float *out_states, void *workspace, size_t workspace_bytes, void *stream,
-                                          const ptgnn_b200_block_plan *bp, int64_t num_source_nodes) {
+                                          const ptgnn_b200_block_plan *bp, int64_t num_source_nodes, void *weight_cache = nullptr,
+                                          size_t weight_cache_bytes = 0, int cache_valid = 0) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int H = in_dim, D = message_dim;
     PTGNN_CHECK_ARG(num_types >= 0 && num_types <= PTGNN_MAX_EDGE_TYPES && (type_off || bp), "mlp_forward: bad num_types=%d",
@@ -589,9 +594,24 @@ static int mlp_forward_impl(const float *node_states, const float *gather_states
     const int ut = use_target_state ? 1 : 0;
     const float *gsrc = gather_states ? gather_states : node_states;   // rows that `src32` indexes (sharded runs)
 
+    // derived weights: in the workspace (re-derived every call) or in the caller's cache (derived when !cache_valid); fused path only
+    char *wsplit = ws + L.wsplit, *dsplit = ws + L.dsplit;
+    bool pack = true;
+    if (fused_path && weight_cache != nullptr) {
+        const size_t need = mlp_fused_cache_bytes(num_types, H, D, out_dim, ut);
+        if (weight_cache_bytes < need) {
+            set_error("mlp_forward_fused: weight cache %zu < required %zu", weight_cache_bytes, need);
+            return PTGNN_E_WORKSPACE;
+        }
+        wsplit = static_cast<char *>(weight_cache);
+        dsplit = wsplit + ws_slice(fused::packed_weight_bytes(3, num_types, H, ut), 1);
+        pack = !cache_valid;
+    }
     if (fused_path) {
-        rc = fused::pack_weights(3, num_types, H, ut, edge_weights, ws + L.wsplit, bp->status, st);
-        if (rc) return rc;
+        if (pack) {
+            rc = fused::pack_weights(3, num_types, H, ut, edge_weights, wsplit, bp->status, st);
+            if (rc) return rc;
+        }
         rc = fused::pack_states(gsrc, num_source_nodes, H, ws + L.xpack, bp->status, st);
         if (rc) return rc;
         const void *tgt_rows = ws + L.xpack;
@@ -603,7 +623,7 @@ static int mlp_forward_impl(const float *node_states, const float *gather_states
         fused::AggregateArgs a{};
         a.nprod = 3; a.src_rows = ws + L.xpack; a.tgt_rows = tgt_rows; a.num_nodes = num_nodes; a.K = H; a.num_types = num_types;
         a.use_target = ut; a.reduce = reduce; a.block_targets = bp->block_targets; a.group_off = bp->group_off; a.src_f = bp->src_f;
-        a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = ws + L.wsplit;
+        a.tl_f = bp->tl_f; a.row_ptr = row_ptr; a.packed_weights = wsplit;
         a.epi = fused::Epilogue{message_activation, ln_weight, ln_bias, ln_eps};
         a.out = y; a.out_mode = 0; a.status = bp->status;
         rc = fused::aggregate(a, st);
@@ -622,7 +642,7 @@ static int mlp_forward_impl(const float *node_states, const float *gather_states
         if (rc) return rc;
     }
     if (!dense_weight) return PTGNN_OK;
-    return dense_any(y, num_nodes, D, dense_weight, dense_bias, out_dim, dense_activation, out_states, ws + L.dsplit, st);
+    return dense_any(y, num_nodes, D, dense_weight, dense_bias, out_dim, dense_activation, out_states, dsplit, st, pack);
 }
 
 extern "C" int ptgnn_b200_mlp_forward_f32(const float *node_states, const float *gather_states, int64_t num_nodes,
@@ -745,6 +765,33 @@ extern "C" int ptgnn_b200_mlp_forward_fused(int32_t bf16_states, const void *nod
                             use_target_state, reduce, message_activation, ln_weight, ln_bias, ln_eps, dense_weight, dense_bias,
                             dense_activation, static_cast<float *>(out_states), workspace, workspace_bytes, stream, block_plan,
                             num_source_nodes);
+}
+
+extern "C" size_t ptgnn_b200_mlp_fused_weight_cache_bytes(int32_t bf16_states, int32_t num_types, int32_t in_dim, int32_t message_dim,
+                                                          int32_t out_dim, int32_t use_target_state) {
+    if (bf16_states || num_types <= 0 || in_dim <= 0 || message_dim <= 0) return 0;
+    if (!(tc_enabled() && fused::supported(3, in_dim, message_dim, use_target_state))) return 0;
+    return mlp_fused_cache_bytes(num_types, in_dim, message_dim, out_dim, use_target_state ? 1 : 0);
+}
+extern "C" int ptgnn_b200_mlp_forward_fused_cached(int32_t bf16_states, const void *node_states, const void *gather_states, int64_t num_nodes,
+                                                   int64_t num_source_nodes, int32_t in_dim, int32_t message_dim, int32_t out_dim,
+                                                   int32_t num_types, const ptgnn_b200_block_plan *block_plan, const int32_t *row_ptr,
+                                                   const float *const *edge_weights, int32_t use_target_state, int32_t reduce,
+                                                   int32_t message_activation, const float *ln_weight, const float *ln_bias, float ln_eps,
+                                                   const float *dense_weight, const float *dense_bias, int32_t dense_activation,
+                                                   void *out_states, void *workspace, size_t workspace_bytes, void *weight_cache,
+                                                   size_t weight_cache_bytes, int32_t cache_valid, void *stream) {
+    if (bf16_states || weight_cache == nullptr)
+        return ptgnn_b200_mlp_forward_fused(bf16_states, node_states, gather_states, num_nodes, num_source_nodes, in_dim, message_dim, out_dim,
+                                            num_types, block_plan, row_ptr, edge_weights, use_target_state, reduce, message_activation,
+                                            ln_weight, ln_bias, ln_eps, dense_weight, dense_bias, dense_activation, out_states, workspace,
+                                            workspace_bytes, stream);
+    PTGNN_CHECK_ARG(block_plan != nullptr, "mlp_forward_fused_cached: null block plan");
+    return mlp_forward_impl(static_cast<const float *>(node_states), static_cast<const float *>(gather_states), num_nodes, in_dim, message_dim,
+                            out_dim, num_types, nullptr, row_ptr, nullptr, nullptr, nullptr, edge_weights, use_target_state, reduce,
+                            message_activation, ln_weight, ln_bias, ln_eps, dense_weight, dense_bias, dense_activation,
+                            static_cast<float *>(out_states), workspace, workspace_bytes, stream, block_plan, num_source_nodes, weight_cache,
+                            weight_cache_bytes, cache_valid);
 }
 
 /* ---- stand-alone pieces (MLP.forward, message MLPs with hidden layers, module aggregators) -------------------------------------- */

@@ -437,16 +437,18 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
 }
 
 int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const float *bias, int Hout, int act, float *out,
-                 void *scratch, cudaStream_t st) {
+                 void *scratch, cudaStream_t st, bool pack) {
     float *w_hi = static_cast<float *>(scratch);
     float *w_lo = reinterpret_cast<float *>(static_cast<char *>(scratch) + ws_slice((size_t)Hout * D, 4));
-    SplitSrc ss{};
-    ss.num = 1; ss.elems = Hout * D; ss.w[0] = W;
-    {
-        TimedScope timed__(PTGNN_KERNEL_PACK, st);
-        split_weights_kernel<<<148, 256, 0, st>>>(ss, w_hi, w_lo);
+    if (pack) {          // the (hi, lo) TF32 split of the weight: skipped when the caller's cache already holds it
+        SplitSrc ss{};
+        ss.num = 1; ss.elems = Hout * D; ss.w[0] = W;
+        {
+            TimedScope timed__(PTGNN_KERNEL_PACK, st);
+            split_weights_kernel<<<148, 256, 0, st>>>(ss, w_hi, w_lo);
+        }
+        PTGNN_LAUNCHED();
     }
-    PTGNN_LAUNCHED();
     DensePolicy::Params p{};
     int rc = make_map_2d(&p.map_y, y, num_nodes, D, D, 128);
     if (!rc) rc = make_map_2d(&p.map_w_hi, w_hi, Hout, D, D, Hout < 128 ? Hout : 128);

@@ -27,7 +27,7 @@ int gru_update(const float *agg, const float *h, int64_t num_nodes, int H, int D
                const float *b_ih, const float *b_hh, float *out, void *scratch, bool pack, cudaStream_t st);
 // out = act(y W^T + b)                                      (scratch >= dense_split_bytes)
 int dense_update(const float *y, int64_t num_nodes, int D, const float *W, const float *bias, int Hout, int act, float *out,
-                 void *scratch, cudaStream_t st);
+                 void *scratch, cudaStream_t st, bool pack = true);
 
 }  // namespace tc
 }  // namespace ptgnn

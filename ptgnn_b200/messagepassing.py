@@ -108,6 +108,48 @@ class AbstractMessagePassingLayer(nn.Module):
         else the identity-keyed cache / a fresh build."""
         return plan_for(adjacency_lists, num_nodes, current_shared_plan(), num_source_nodes)
 
+    # ---- derived-weight cache ------------------------------------------------------------------------------------------
+    def _weight_cache(self, kind: str, nbytes: int, params: List[torch.Tensor], device: torch.device):
+        """Returns (buffer or None, valid).  The buffer holds the kernels' working copies of the parameters (TF32 hi/lo
+        splits and the gate-blocked GRU packing, or their bf16 versions); it is valid while no parameter has been
+        modified in place (`Tensor._version`), re-assigned (`data_ptr`) or moved since the call that filled it.  All
+        uses are ordered on the layer's CUDA stream; a call on a different stream refills the buffer."""
+        if nbytes <= 0:
+            return None, False
+        stream = torch.cuda.current_stream(device).cuda_stream
+        def version(p: torch.Tensor):
+            try:
+                return p._version
+            except RuntimeError:        # inference tensors carry no version counter: never reuse
+                return object()
+
+        key = (tuple((p.data_ptr(), version(p)) for p in params), nbytes, stream)
+        if not hasattr(self, "_derived_weights"):
+            self._derived_weights = {}
+        entry = self._derived_weights.get((kind, device))
+        if entry is None or entry["buf"].numel() != nbytes:
+            entry = {"buf": torch.empty(nbytes, dtype=torch.uint8, device=device), "key": None, "pending": None}
+            self._derived_weights[(kind, device)] = entry
+        # eval mode only: in-place edits made through `param.data` do not move the version counter, and training loops
+        # are where those happen -- in training mode the copies are simply re-derived every call
+        valid = (not self.training) and entry["key"] == key
+        entry["pending"] = key
+        return entry["buf"], valid
+
+    def invalidate_weight_cache(self) -> None:
+        """Forget the derived copies (needed only after editing parameters through `.data` in eval mode)."""
+        self._derived_weights = {}
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_derived_weights"] = {}      # device scratch, not part of the module's state
+        return state
+
+    def _weight_cache_filled(self, kind: str, device: torch.device) -> None:
+        entry = getattr(self, "_derived_weights", {}).get((kind, device))
+        if entry is not None and entry["pending"] is not None:
+            entry["key"], entry["pending"] = entry["pending"], None
+
     def _apply(self, fn, *args, **kwargs):
         # .to() / .cuda() / .float(): device copies of the parameters derived for the old placement are dead
         if hasattr(self, "_derived_weights"):
@@ -325,46 +367,6 @@ class GatedMessagePassingLayer(AbstractMessagePassingLayer):
         agg = C.segment_reduce(msg, plan, reduce)
         return C.grucell(agg, h, self.__state_update)
 
-    # ---- derived-weight cache ------------------------------------------------------------------------------------------
-    def _weight_cache(self, kind: str, nbytes: int, params: List[torch.Tensor], device: torch.device):
-        """Returns (buffer or None, valid).  The buffer holds the kernels' working copies of the parameters (TF32 hi/lo
-        splits and the gate-blocked GRU packing, or their bf16 versions); it is valid while no parameter has been
-        modified in place (`Tensor._version`), re-assigned (`data_ptr`) or moved since the call that filled it.  All
-        uses are ordered on the layer's CUDA stream; a call on a different stream refills the buffer."""
-        if nbytes <= 0:
-            return None, False
-        stream = torch.cuda.current_stream(device).cuda_stream
-        def version(p: torch.Tensor):
-            try:
-                return p._version
-            except RuntimeError:        # inference tensors carry no version counter: never reuse
-                return object()
-
-        key = (tuple((p.data_ptr(), version(p)) for p in params), nbytes, stream)
-        entry = self._derived_weights.get((kind, device))
-        if entry is None or entry["buf"].numel() != nbytes:
-            entry = {"buf": torch.empty(nbytes, dtype=torch.uint8, device=device), "key": None, "pending": None}
-            self._derived_weights[(kind, device)] = entry
-        # eval mode only: in-place edits made through `param.data` do not move the version counter, and training loops
-        # are where those happen -- in training mode the copies are simply re-derived every call
-        valid = (not self.training) and entry["key"] == key
-        entry["pending"] = key
-        return entry["buf"], valid
-
-    def invalidate_weight_cache(self) -> None:
-        """Forget the derived copies (needed only after editing parameters through `.data` in eval mode)."""
-        self._derived_weights = {}
-
-    def __getstate__(self):
-        state = self.__dict__.copy()
-        state["_derived_weights"] = {}      # device scratch, not part of the module's state
-        return state
-
-    def _weight_cache_filled(self, kind: str, device: torch.device) -> None:
-        entry = self._derived_weights.get((kind, device))
-        if entry is not None and entry["pending"] is not None:
-            entry["key"], entry["pending"] = entry["pending"], None
-
     @property
     def input_state_dimension(self) -> int:
         return self.__state_dimension
@@ -568,13 +570,20 @@ class MlpMessagePassingLayer(AbstractMessagePassingLayer):
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=h.device)
             out = torch.empty(num_nodes, out_dim, dtype=state_dtype, device=h.device)
             bp = plan.block_plan()
+            # derived copies of the edge weights (fp16 hi | lo' in the kernel's TMEM order) and of the dense weight (TF32 hi / lo): once
+            # per parameter version, like the gated layer's (fp32 path; the bf16 path converts per call)
+            cache_params = weights + ([d_w] if d_w is not None else [])
+            cache, valid = self._weight_cache("mlp_f32_fused", 0 if bf16 else lib.ptgnn_b200_mlp_fused_weight_cache_bytes(
+                0, plan.num_types, H, D, out_dim, ut_i), cache_params, h.device)
             with torch.cuda.device(h.device):
-                rc = lib.ptgnn_b200_mlp_forward_fused(
+                rc = lib.ptgnn_b200_mlp_forward_fused_cached(
                     int(bf16), N.ptr(h), N.ptr(gsrc), num_nodes, ns, H, D, out_dim, plan.num_types, ctypes.byref(bp), N.ptr(plan.row_ptr),
                     N.ptr_table(weights), ut_i, reduce, msg_act, N.ptr(ln_w), N.ptr(ln_b), float(ln.eps) if ln is not None else 0.0,
-                    N.ptr(d_w), N.ptr(d_b), dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.current_stream(h.device),
+                    N.ptr(d_w), N.ptr(d_b), dense_act, N.ptr(out), N.ptr(ws), ws_bytes, N.ptr(cache), 0 if cache is None else cache.numel(),
+                    int(valid), N.current_stream(h.device),
                 )
-            N.check(rc, "ptgnn_b200_mlp_forward_fused")
+            N.check(rc, "ptgnn_b200_mlp_forward_fused_cached")
+            self._weight_cache_filled("mlp_f32_fused", h.device)
             return apply_dropout(out)
         if state_dtype == torch.bfloat16:   # bf16 states, fp32 parameters (converted inside the library), fp32 accumulation
             ut = int(self.__use_target_state_as_message_input)

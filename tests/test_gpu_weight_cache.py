@@ -54,3 +54,34 @@ def test_weight_cache_reuse_and_invalidation(dtype):
         layer(h, adj)
         l4 = N.launch_count()
     assert (l4 - l3) == (l1 - l0)
+
+
+def test_mlp_layer_derived_weight_cache():
+    """MlpMessagePassingLayer (fused fp32 path): packed edge weights + split dense weight are derived once per parameter version."""
+    import ptgnn_b200 as P
+    from ptgnn_b200 import _native as N
+    from helpers import random_adjacency
+
+    gen = torch.Generator().manual_seed(6)
+    torch.manual_seed(6)
+    n, counts, H = 3000, [8000, 2500, 0, 40], 128
+    adj = [(s.cuda(), t.cuda()) for s, t in random_adjacency(gen, n, counts)]
+    h = torch.randn(n, H, generator=gen).cuda()
+    layer = P.MlpMessagePassingLayer(H, H, H, len(counts), "max").cuda().eval()
+    with torch.no_grad():
+        P.MlpMessagePassingLayer(H, H, H, len(counts), "max").cuda().eval()(h, adj)     # builds the plan of `adj`
+        l0 = N.launch_count()
+        first = layer(h, adj)
+        l1 = N.launch_count()
+        again = layer(h, adj)
+        l2 = N.launch_count()
+        assert torch.equal(first, again)
+        assert (l1 - l0) - (l2 - l1) == 2, f"the cached call must skip the two weight-derivation launches ({l1 - l0} vs {l2 - l1})"
+        for p in layer.parameters():
+            p.mul_(1.5)                                                                   # optimiser step / load_state_dict
+        changed = layer(h, adj)
+        l3 = N.launch_count()
+        assert (l3 - l2) == (l1 - l0) and not torch.equal(changed, first)
+        fresh = P.MlpMessagePassingLayer(H, H, H, len(counts), "max").cuda().eval()
+        fresh.load_state_dict(layer.state_dict())
+        assert torch.equal(fresh(h, adj), changed)                                        # the re-derived copies are the right ones
