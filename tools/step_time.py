@@ -26,8 +26,13 @@ dtype = sys.argv[1] if len(sys.argv) > 1 else "f32"
 label = sys.argv[2] if len(sys.argv) > 2 else ""
 b = graph2class_batch()
 torch.manual_seed(0)
-layers = [P.GatedMessagePassingLayer(128, 128, 17, "sum") for _ in range(8)]
+if os.environ.get("STEP_LAYERS") == "mlp":        # the VarMisuse-style stack; STEP_NOCACHE=1: training mode (derived weights re-made per call)
+    layers = [P.MlpMessagePassingLayer(128, 128, 128, 17, "max") for _ in range(8)]
+else:
+    layers = [P.GatedMessagePassingLayer(128, 128, 17, "sum") for _ in range(8)]
 gnn = P.GraphNeuralNetwork(layers, torch.nn.Identity(), True, True).cuda().eval()
+if os.environ.get("STEP_NOCACHE") == "1":
+    gnn.train()
 h = torch.randn(b.num_nodes, 128).cuda()
 if dtype == "bf16":
     h = h.to(torch.bfloat16)
@@ -55,4 +60,12 @@ with torch.no_grad():
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
 times.sort()
+N.kernel_timing(True)
+N.read_kernel_timing()
+with torch.no_grad():
+    for _ in range(5):
+        step()
+kt = N.read_kernel_timing()
+N.kernel_timing(False)
+print("   kernels: " + "  ".join(f"{k} {v[0] / max(v[1], 1):.4f} ms x{v[1] // 5}" for k, v in kt.items() if v[1]))
 print(f"{dtype} chain={os.environ.get('PTGNN_B200_CHAIN', '1')} {label}: step median {times[len(times) // 2]:.3f} ms  min {times[0]:.3f}  p90 {times[17]:.3f}")
